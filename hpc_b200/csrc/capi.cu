@@ -1,0 +1,241 @@
+// capi.cu — the extern "C" layer declared in include/spmm_b200.h.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.h"
+
+namespace spmm_b200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    // same information the reference prints before exiting (PA4/handout/include/util.h:63-84)
+    set_error("Cuda failure: %s (%d) in %s at %s:%d", cudaGetErrorString(e), (int)e, what, file, line);
+    return (int)e;
+}
+
+}  // namespace spmm_b200
+
+using namespace spmm_b200;
+
+extern "C" {
+
+const char *spmm_b200_last_error(void) { return g_err; }
+
+int spmm_b200_create(const int *d_ptr, const int *d_idx, const float *d_val, int num_v, int num_e,
+                     int feat_in, spmm_b200_t *out) {
+    if (!out || num_v < 0 || num_e < 0 || feat_in < 0 || (num_v > 0 && !d_ptr) ||
+        (num_e > 0 && (!d_idx || !d_val))) {
+        set_error("spmm_b200_create: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    spmm_b200_handle *h = new (std::nothrow) spmm_b200_handle();
+    if (!h) {
+        set_error("spmm_b200_create: out of host memory");
+        return SPMM_B200_ENOMEM;
+    }
+    h->d_ptr = d_ptr;
+    h->d_idx = d_idx;
+    h->d_val = d_val;
+    h->num_v = num_v;
+    h->num_e = num_e;
+    h->feat = feat_in;
+    *out = h;
+    return 0;
+}
+
+int spmm_b200_set_feat(spmm_b200_t h, int feat_in) {
+    if (!h || feat_in < 0) {
+        set_error("spmm_b200_set_feat: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    h->feat = feat_in;
+    free_plan(h->plan);
+    return 0;
+}
+
+int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
+    if (!h || !name) {
+        set_error("spmm_b200_set_option: null argument");
+        return SPMM_B200_EINVAL;
+    }
+    if (!strcmp(name, "seg_len") && value >= 0) h->opt_seg_len = value;
+    else if (!strcmp(name, "kslice") && value >= 0 && value % 4 == 0) h->opt_kslice = value;
+    else if (!strcmp(name, "block") && value >= 32 && value <= 256 && value % 32 == 0) h->opt_block = value;
+    else if (!strcmp(name, "reorder") && (value == 0 || value == 1)) h->opt_reorder = value;
+    else {
+        set_error("spmm_b200_set_option: unknown option or bad value: %s = %lld", name, value);
+        return SPMM_B200_EINVAL;
+    }
+    h->plan.ready = false;
+    return 0;
+}
+
+int spmm_b200_preprocess(spmm_b200_t h, const float *vin, float *vout, void *stream) {
+    (void)vin;
+    (void)vout;
+    if (!h) {
+        set_error("spmm_b200_preprocess: null handle");
+        return SPMM_B200_EINVAL;
+    }
+    return build_plan(h, (cudaStream_t)stream);
+}
+
+int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream) {
+    if (!h) {
+        set_error("spmm_b200_run: null handle");
+        return SPMM_B200_EINVAL;
+    }
+    if (!h->plan.ready) {
+        set_error("spmm_b200_run: preprocess has not been called");
+        return SPMM_B200_ESTATE;
+    }
+    if ((size_t)h->num_v * h->feat > 0 && (!vin || !vout)) {
+        set_error("spmm_b200_run: null vin/vout");
+        return SPMM_B200_EINVAL;
+    }
+    if (!h->plan.scalar && (((uintptr_t)vin | (uintptr_t)vout) & 15)) {
+        set_error("spmm_b200_run: vin/vout must be 16-byte aligned");
+        return SPMM_B200_EINVAL;
+    }
+    return launch_spmm(h, vin, vout, (cudaStream_t)stream, &h->plan.launches);
+}
+
+int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *stream) {
+    if (!h || !h_vin || !h_vout) {
+        set_error("spmm_b200_run_host: null argument");
+        return SPMM_B200_EINVAL;
+    }
+    if (!h->plan.ready) {
+        set_error("spmm_b200_run_host: preprocess has not been called");
+        return SPMM_B200_ESTATE;
+    }
+    const size_t n = (size_t)h->num_v * h->feat;
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->stage_elems < n) {
+        cudaFree(h->d_stage_in);
+        cudaFree(h->d_stage_out);
+        h->d_stage_in = h->d_stage_out = nullptr;
+        h->stage_elems = 0;
+        SB_CUDA(cudaMalloc((void **)&h->d_stage_in, n * sizeof(float)));
+        SB_CUDA(cudaMalloc((void **)&h->d_stage_out, n * sizeof(float)));
+        h->stage_elems = n;
+    }
+    SB_CUDA(cudaMemcpyAsync(h->d_stage_in, h_vin, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = launch_spmm(h, h->d_stage_in, h->d_stage_out, s, &h->plan.launches);
+    if (rc) return rc;
+    SB_CUDA(cudaMemcpyAsync(h_vout, h->d_stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int spmm_b200_destroy(spmm_b200_t h) {
+    if (!h) return 0;
+    free_plan(h->plan);
+    cudaFree(h->d_stage_in);
+    cudaFree(h->d_stage_out);
+    delete h;
+    return 0;
+}
+
+int spmm_b200_launches_per_run(spmm_b200_t h) { return h ? h->plan.launches : 0; }
+
+int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info) {
+    if (!h || !info || !h->plan.ready) {
+        set_error("spmm_b200_plan_info: no plan");
+        return h && info ? SPMM_B200_ESTATE : SPMM_B200_EINVAL;
+    }
+    const Plan &p = h->plan;
+    info->num_v = h->num_v;
+    info->num_e = h->num_e;
+    info->feat_in = h->feat;
+    info->seg_len = p.seg_len;
+    info->kslice = p.kslice;
+    info->n_slices = p.n_slices;
+    info->block = p.block;
+    info->n_light = p.n_light;
+    info->n_heavy = p.n_heavy;
+    info->n_seg = p.n_seg;
+    info->panel_len = p.panel_len;
+    info->lanes = p.lanes;
+    info->vec = p.vec;
+    return 0;
+}
+
+int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) {
+    if (!h || !h->plan.ready) {
+        set_error("spmm_b200_plan_copy: no plan");
+        return SPMM_B200_ESTATE;
+    }
+    const Plan &p = h->plan;
+    const void *src = nullptr;
+    size_t want = 0;
+    switch (which) {
+        case 0: src = p.d_row_perm; want = sizeof(int) * (size_t)p.n_light; break;
+        case 1: src = p.d_heavy_rows; want = sizeof(int) * (size_t)p.n_heavy; break;
+        case 2: src = p.d_heavy_seg0; want = p.n_heavy ? sizeof(int) * ((size_t)p.n_heavy + 1) : 0; break;
+        case 3: src = p.d_seg_desc; want = sizeof(SegDesc) * (size_t)p.n_seg; break;
+        case 4: src = p.d_panel; want = sizeof(int2) * (size_t)p.panel_len; break;
+        default: set_error("spmm_b200_plan_copy: unknown array %d", which); return SPMM_B200_EINVAL;
+    }
+    if (bytes != want) {
+        set_error("spmm_b200_plan_copy: array %d is %zu bytes, caller gave %zu", which, want, bytes);
+        return SPMM_B200_EINVAL;
+    }
+    if (want == 0) return 0;
+    if (!src) {   // natural order: row_perm is implicit
+        if (which == 0) {
+            int *dst = (int *)host_dst;
+            for (int i = 0; i < p.n_light; ++i) dst[i] = i;
+            return 0;
+        }
+        set_error("spmm_b200_plan_copy: array %d is empty", which);
+        return SPMM_B200_ESTATE;
+    }
+    SB_CUDA(cudaMemcpy(host_dst, src, want, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int spmm_b200_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream_id, float mean,
+                          float stddev, void *stream) {
+    if (n < 0 || (n > 0 && !d_dst)) {
+        set_error("spmm_b200_fill_normal: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    return launch_fill_normal(d_dst, n, seed, stream_id, mean, stddev, (cudaStream_t)stream);
+}
+
+int spmm_b200_valid(const float *d_y, const float *d_y2, long long num, long long *mismatches, void *stream) {
+    if (!mismatches || num < 0 || (num > 0 && (!d_y || !d_y2))) {
+        set_error("spmm_b200_valid: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *d_count = nullptr;
+    SB_CUDA(cudaMalloc((void **)&d_count, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s);
+    int rc = 0;
+    if (e == cudaSuccess) rc = launch_valid(d_y, d_y2, num, d_count, s);
+    unsigned long long host = 0;
+    if (e == cudaSuccess && rc == 0)
+        e = cudaMemcpyAsync(&host, d_count, sizeof(host), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(s);
+    cudaFree(d_count);
+    if (rc) return rc;
+    SB_CUDA(e);
+    *mismatches = (long long)host;
+    return 0;
+}
+
+}  // extern "C"

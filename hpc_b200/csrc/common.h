@@ -1,0 +1,112 @@
+// common.h — internal declarations shared by the engine's translation units (not installed).
+#ifndef HPC_B200_COMMON_H_
+#define HPC_B200_COMMON_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "spmm_b200.h"
+
+namespace spmm_b200 {
+
+// Error plumbing: the reference aborts in checkCudaErrors (PA4/handout/include/util.h:63-84);
+// the C ABI records the message and returns the code instead.
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SB_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return ::spmm_b200::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// One heavy-row segment: `len` nonzeros of `row` starting at CSR position `nnz_begin`,
+// staged at panel[panel_off .. panel_off + roundup2(len)).
+struct SegDesc {
+    int row;
+    int panel_off;
+    int len;
+    int nnz_begin;
+};
+
+// Everything a run needs, passed to the kernels by value.
+struct RunArgs {
+    const int *ptr;
+    const int *idx;
+    const float *val;
+    const float *vin;
+    float *vout;
+    int num_v;
+    int feat;        // K
+    int kslice;      // feature columns per pass
+    int n_slices;
+    // light rows
+    const int *row_perm;   // NULL = natural order
+    int n_light;
+    int light_tasks_per_slice;   // warps per slice
+    // heavy rows
+    const SegDesc *seg_desc;
+    const int2 *panel;
+    float *part;           // [n_seg][K] partial sums
+    int n_seg;
+    const int *heavy_rows;
+    const int *heavy_seg0;
+    int n_heavy;
+};
+
+struct Plan {
+    bool ready = false;
+    int seg_len = 0, kslice = 0, n_slices = 0, block = 256, lanes = 0, vec = 0;
+    bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
+    int n_light = 0, n_heavy = 0, n_seg = 0;
+    long long panel_len = 0;
+    int *d_row_perm = nullptr;
+    int *d_heavy_rows = nullptr;
+    int *d_heavy_seg0 = nullptr;
+    SegDesc *d_seg_desc = nullptr;
+    int2 *d_panel = nullptr;
+    float *d_part = nullptr;
+    int launches = 0;
+};
+
+}  // namespace spmm_b200
+
+struct spmm_b200_handle {
+    const int *d_ptr = nullptr;
+    const int *d_idx = nullptr;
+    const float *d_val = nullptr;
+    int num_v = 0, num_e = 0, feat = 0;
+    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 256, opt_reorder = 1;
+    spmm_b200::Plan plan;
+    float *d_stage_in = nullptr, *d_stage_out = nullptr;
+    size_t stage_elems = 0;
+};
+
+namespace spmm_b200 {
+
+// preprocess.cu
+int build_plan(spmm_b200_handle *h, cudaStream_t stream);
+void free_plan(Plan &p);
+
+// spmm_kernels.cu
+int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
+                int *launches);
+int launch_build_panel(const SegDesc *d_seg, int n_seg, const int *d_idx, const float *d_val,
+                       int2 *d_panel, cudaStream_t stream);
+int launch_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream_id, float mean,
+                       float stddev, cudaStream_t stream);
+int launch_valid(const float *d_y, const float *d_y2, long long num, unsigned long long *d_count,
+                 cudaStream_t stream);
+
+// lanes/vec choice for a slice width (shared by plan + launch)
+inline void shape_for_kslice(int kslice, int *lanes, int *vec) {
+    // kslice is a multiple of 4; lanes*vec*4 >= kslice, lanes a power of two <= 32
+    int q = (kslice + 3) / 4;   // float4 per row slice
+    int l = 1;
+    while (l < q && l < 32) l <<= 1;
+    *lanes = l;
+    *vec = (q + l - 1) / l;     // 1 for kslice <= 128, 2 for 256
+}
+
+}  // namespace spmm_b200
+#endif

@@ -1,0 +1,208 @@
+// preprocess.cu — builds the execution plan of one (CSR, K) pair.
+//
+// Takes the place of the student's SpMMOpt::preprocess (PA4/workspace/src/spmm_opt.cu:37-69:
+// copy ptr to the host, cut every row into <=256-nnz tasks, random_shuffle, upload, memset
+// vout). The plan here is deterministic and fully specified so the CPU oracle
+// (oracle/plan_oracle.py) can restate it and the tests compare bit for bit:
+//
+//   deg(r)    = ptr[r+1] - ptr[r]
+//   heavy(r)  = deg(r) > seg_len
+//   bucket(r) = bit length of deg(r)                      (0 for an empty row)
+//   order     = rows by (bucket descending, r ascending)  (natural order when reorder = 0)
+//   row_perm  = the non-heavy rows in that order
+//   heavy rows, in that order, are cut into nseg = ceil(deg/seg_len) nnz-balanced segments
+//               [begin + floor(j*deg/nseg), begin + floor((j+1)*deg/nseg)),  j = 0..nseg-1
+//   panel     = the segments' {col, val} pairs back to back, each segment padded to an even
+//               number of entries (16-byte granules for the 1-D TMA copies), pad = {0, 0.0f}
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.h"
+
+namespace spmm_b200 {
+
+void free_plan(Plan &p) {
+    cudaFree(p.d_row_perm);
+    cudaFree(p.d_heavy_rows);
+    cudaFree(p.d_heavy_seg0);
+    cudaFree(p.d_seg_desc);
+    cudaFree(p.d_panel);
+    cudaFree(p.d_part);
+    p = Plan();
+}
+
+static inline int bit_length(unsigned x) { return x ? 32 - __builtin_clz(x) : 0; }
+
+int auto_seg_len(long long nnz) {
+    // long enough to amortise the segment prologue, short enough that the longest task is a
+    // small share of one SM's work: next power of two of nnz/16384, clamped to [256, 4096]
+    long long t = nnz / 16384;
+    int l = 256;
+    while (l < t && l < 4096) l <<= 1;
+    return l;
+}
+
+int auto_kslice(int num_v, int feat) {
+    if (feat % 4 != 0) return feat;
+    // widest slice whose share of B (num_v * kslice * 4 bytes) stays well inside the 126 MB L2
+    const long long budget = 48ll << 20;
+    int ks = 256;
+    while (ks > 32 && (long long)num_v * ks * 4 > budget) ks >>= 1;
+    if (ks > feat) {
+        ks = (feat + 3) & ~3;
+    }
+    return ks;
+}
+
+// Host-only core of the plan (also exported as spmm_b200_plan_host for CPU-side tests).
+int plan_rows_host(const int *ptr, int M, int seg_len, int reorder, std::vector<int> &row_perm,
+                   std::vector<int> &heavy_rows, std::vector<int> &heavy_seg0, std::vector<SegDesc> &segs,
+                   long long *panel_len_out) {
+    // stable counting sort by bucket, descending
+    std::vector<int> order((size_t)M);
+    if (reorder) {
+        size_t cnt[34] = {0};
+        for (int r = 0; r < M; ++r) {
+            const int d = ptr[r + 1] - ptr[r];
+            if (d < 0) {
+                set_error("CSR ptr decreases at row %d", r);
+                return SPMM_B200_EINVAL;
+            }
+            ++cnt[bit_length((unsigned)d)];
+        }
+        size_t start[34];
+        size_t run = 0;
+        for (int b = 33; b >= 0; --b) {
+            start[b] = run;
+            run += cnt[b];
+        }
+        for (int r = 0; r < M; ++r) order[start[bit_length((unsigned)(ptr[r + 1] - ptr[r]))]++] = r;
+    } else {
+        for (int r = 0; r < M; ++r) order[r] = r;
+    }
+
+    row_perm.clear();
+    heavy_rows.clear();
+    heavy_seg0.clear();
+    segs.clear();
+    row_perm.reserve(M);
+    long long panel_len = 0;
+    for (int k = 0; k < M; ++k) {
+        const int r = order[k];
+        const int begin = ptr[r];
+        const int d = ptr[r + 1] - begin;
+        if (d <= seg_len) {
+            row_perm.push_back(r);
+            continue;
+        }
+        heavy_rows.push_back(r);
+        heavy_seg0.push_back((int)segs.size());
+        const int nseg = (int)(((long long)d + seg_len - 1) / seg_len);
+        for (int j = 0; j < nseg; ++j) {
+            const int b = begin + (int)((long long)j * d / nseg);
+            const int e = begin + (int)((long long)(j + 1) * d / nseg);
+            SegDesc s;
+            s.row = r;
+            s.panel_off = (int)panel_len;
+            s.len = e - b;
+            s.nnz_begin = b;
+            segs.push_back(s);
+            panel_len += (s.len + 1) & ~1;
+        }
+    }
+    if (!heavy_rows.empty()) heavy_seg0.push_back((int)segs.size());
+    if (panel_len > 0x7fffffffll) {
+        set_error("panel too large");
+        return SPMM_B200_EINVAL;
+    }
+    *panel_len_out = panel_len;
+    return 0;
+}
+
+int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
+    Plan &p = h->plan;
+    free_plan(p);
+    const int M = h->num_v, K = h->feat;
+    p.block = (int)h->opt_block;
+    p.scalar = (K % 4) != 0;
+    p.kslice = h->opt_kslice > 0 ? (int)h->opt_kslice : auto_kslice(M, K);
+    if (p.scalar) p.kslice = K;
+    if (p.kslice > 256) p.kslice = 256;
+    if (K > 0 && p.kslice > ((K + 3) & ~3)) p.kslice = (K + 3) & ~3;
+    p.n_slices = (K > 0) ? (K + p.kslice - 1) / p.kslice : 0;
+    if (!p.scalar && K > 0) shape_for_kslice(p.kslice, &p.lanes, &p.vec);
+    p.seg_len = h->opt_seg_len > 0 ? (int)h->opt_seg_len : auto_seg_len(h->num_e);
+    if (p.scalar) p.seg_len = 0x7fffffff;   // scalar fallback keeps every row whole
+
+    std::vector<int> ptr((size_t)M + 1, 0);
+    if (M > 0) {
+        SB_CUDA(cudaMemcpyAsync(ptr.data(), h->d_ptr, sizeof(int) * ((size_t)M + 1), cudaMemcpyDeviceToHost,
+                                stream));
+        SB_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (M > 0 && (ptr[0] != 0 || ptr[M] != h->num_e)) {
+        set_error("CSR ptr is inconsistent: ptr[0]=%d ptr[num_v]=%d num_e=%d", ptr[0], ptr[M], h->num_e);
+        return SPMM_B200_EINVAL;
+    }
+
+    std::vector<int> row_perm, heavy_rows, heavy_seg0;
+    std::vector<SegDesc> segs;
+    long long panel_len = 0;
+    int rc = plan_rows_host(ptr.data(), M, p.seg_len, (int)h->opt_reorder, row_perm, heavy_rows, heavy_seg0, segs,
+                            &panel_len);
+    if (rc) return rc;
+    p.n_light = (int)row_perm.size();
+    p.n_heavy = (int)heavy_rows.size();
+    p.n_seg = (int)segs.size();
+    p.panel_len = panel_len;
+
+    auto upload = [&](void **dst, const void *src, size_t bytes) -> int {
+        if (bytes == 0) return 0;
+        SB_CUDA(cudaMalloc(dst, bytes));
+        SB_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return 0;
+    };
+    if (h->opt_reorder || p.n_heavy > 0) {
+        if ((rc = upload((void **)&p.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
+    }
+    if (p.n_heavy > 0) {
+        if ((rc = upload((void **)&p.d_heavy_rows, heavy_rows.data(), sizeof(int) * heavy_rows.size()))) return rc;
+        if ((rc = upload((void **)&p.d_heavy_seg0, heavy_seg0.data(), sizeof(int) * heavy_seg0.size()))) return rc;
+        if ((rc = upload((void **)&p.d_seg_desc, segs.data(), sizeof(SegDesc) * segs.size()))) return rc;
+        SB_CUDA(cudaMalloc((void **)&p.d_panel, sizeof(int2) * (size_t)panel_len));
+        SB_CUDA(cudaMalloc((void **)&p.d_part, sizeof(float) * (size_t)p.n_seg * K));
+        if ((rc = launch_build_panel(p.d_seg_desc, p.n_seg, h->d_idx, h->d_val, p.d_panel, stream))) return rc;
+    }
+    SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+    p.ready = true;
+    return 0;
+}
+
+}  // namespace spmm_b200
+
+// Host-only plan for CPU-side callers and tests (declared in include/spmm_b200.h).
+extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, long long seg_len, int reorder, int *row_perm,
+                                   int *n_light, int *heavy_rows, int *n_heavy, int *heavy_seg0, int *seg_desc,
+                                   int *n_seg, long long *panel_len) {
+    using namespace spmm_b200;
+    if (!h_ptr || num_v < 0 || !n_light || !n_heavy || !n_seg || !panel_len) {
+        set_error("spmm_b200_plan_host: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    if (seg_len <= 0) seg_len = auto_seg_len(h_ptr[num_v]);
+    if (seg_len > 0x7fffffffll) seg_len = 0x7fffffffll;
+    std::vector<int> rp, hr, hs;
+    std::vector<SegDesc> segs;
+    int rc = plan_rows_host(h_ptr, num_v, (int)seg_len, reorder, rp, hr, hs, segs, panel_len);
+    if (rc) return rc;
+    *n_light = (int)rp.size();
+    *n_heavy = (int)hr.size();
+    *n_seg = (int)segs.size();
+    if (row_perm) std::copy(rp.begin(), rp.end(), row_perm);
+    if (heavy_rows) std::copy(hr.begin(), hr.end(), heavy_rows);
+    if (heavy_seg0) std::copy(hs.begin(), hs.end(), heavy_seg0);
+    if (seg_desc && !segs.empty()) memcpy(seg_desc, segs.data(), sizeof(SegDesc) * segs.size());
+    return 0;
+}

@@ -1,0 +1,491 @@
+// spmm_kernels.cu — sm_100a kernels of the CSR SpMM engine.
+//
+// Replaces spmm_kernel_ref (PA4/handout/src/spmm_ref.cu:3-17: one thread per row, serial over
+// K and over the row) and the student's SpmmOptKernel (PA4/workspace/src/spmm_opt.cu:9-35:
+// one CTA per <=256-nnz task, atomicAdd into a pre-zeroed vout).
+//
+//   spmm_light_kernel  rows kept whole. LANES lanes cooperate on one row, each owning VEC
+//                      float4 of the feature slice, so a warp covers 32/LANES rows at once.
+//                      col/val are read coalesced, LANES at a time, and broadcast by shuffle;
+//                      B rows are gathered with 128-bit loads; every output element is one
+//                      in-order FMA chain from 0.0f — the same chain as spmm_ref.cu:10-14, so
+//                      the result is bit-identical to the reference for these rows.
+//   spmm_heavy_kernel  rows split into nnz-balanced segments (one warp per segment). The
+//                      segment's {col,val} panel is staged into shared memory with 1-D TMA
+//                      (cp.async.bulk + mbarrier, double buffered); the 32/LANES lane groups
+//                      take alternate nonzeros and are combined by warp shuffles.
+//   spmm_fixup_kernel  adds a heavy row's segment partials in segment order (deterministic,
+//                      no atomics, vout never needs pre-zeroing).
+//
+// fp32 CUDA cores only: SpMM is a gather, not a dense contraction.
+#include <stdio.h>
+
+#include "common.h"
+
+namespace spmm_b200 {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kChunk = 128;   // panel entries per TMA stage (1 KB)
+constexpr int kStages = 2;
+
+// ---- memory helpers ------------------------------------------------------------------------
+
+// col/val are streamed exactly once per slice: keep them out of L1 so B rows stay there.
+__device__ __forceinline__ int ld_stream_s32(const int *p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_b_row(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+__device__ __forceinline__ void st_c_row(float *p, const float4 &v) {
+    __stcs(reinterpret_cast<float4 *>(p), v);
+}
+__device__ __forceinline__ void fma4(float4 &acc, const float4 &b, float v) {
+    acc.x = fmaf(b.x, v, acc.x);
+    acc.y = fmaf(b.y, v, acc.y);
+    acc.z = fmaf(b.z, v, acc.z);
+    acc.w = fmaf(b.w, v, acc.w);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D TMA: global -> shared, completion counted in bytes on the mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- light rows ----------------------------------------------------------------------------
+
+template <int LANES, int VEC>
+__global__ void __launch_bounds__(256) spmm_light_kernel(const RunArgs a) {
+    constexpr int GROUPS = 32 / LANES;
+    constexpr int UMAX = (VEC == 1) ? 8 : 4;
+    constexpr int U = LANES < UMAX ? LANES : UMAX;   // gathers in flight per lane group
+    static_assert(LANES % U == 0, "unroll must tile the chunk");
+    const int lane = threadIdx.x & 31;
+    const int l = lane % LANES;
+    const int g = lane / LANES;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int slice = (int)(gw / a.light_tasks_per_slice);
+    if (slice >= a.n_slices) return;
+    const int task = (int)(gw - (long long)slice * a.light_tasks_per_slice);
+    const int slot = task * GROUPS + g;
+
+    int row = -1, begin = 0, deg = 0;
+    if (slot < a.n_light) {
+        row = a.row_perm ? a.row_perm[slot] : slot;
+        begin = a.ptr[row];
+        deg = a.ptr[row + 1] - begin;
+    }
+    int maxdeg = deg;
+#pragma unroll
+    for (int off = LANES; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(kFull, maxdeg, off));
+
+    const int K = a.feat;
+    const int col0 = slice * a.kslice + l * 4;
+    const int col_end = min(K, (slice + 1) * a.kslice);
+    const float *bbase = a.vin + col0;
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool colok[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) colok[v] = col0 + v * LANES * 4 < col_end;
+
+    for (int base = 0; base < maxdeg; base += LANES) {
+        const int i = base + l;
+        int c = 0;
+        float w = 0.f;
+        if (i < deg) {
+            c = ld_stream_s32(a.idx + begin + i);
+            w = ld_stream_f32(a.val + begin + i);
+        }
+        const int n = min(LANES, maxdeg - base);   // warp-uniform
+        for (int t0 = 0; t0 < n; t0 += U) {
+            float4 b[U][VEC];
+            float wt[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u;
+                const int ct = __shfl_sync(kFull, c, t, LANES);
+                wt[u] = __shfl_sync(kFull, w, t, LANES);
+                ok[u] = base + t < deg;
+                const float *brow = bbase + (size_t)ct * K;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (ok[u] && colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (ok[u] && colok[v]) fma4(acc[v], b[u][v], wt[u]);
+            }
+        }
+    }
+    if (row >= 0) {
+        float *crow = a.vout + (size_t)row * K + col0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (colok[v]) st_c_row(crow + v * LANES * 4, acc[v]);
+    }
+}
+
+// K % 4 != 0: scalar lanes over the feature columns, one warp per row, same in-order chain.
+__global__ void __launch_bounds__(256) spmm_scalar_kernel(const RunArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= a.n_light) return;
+    const int row = a.row_perm ? a.row_perm[gw] : (int)gw;
+    const int begin = a.ptr[row];
+    const int deg = a.ptr[row + 1] - begin;
+    const int K = a.feat;
+    for (int cb = 0; cb < K; cb += 32) {
+        const int col = cb + lane;
+        float acc = 0.f;
+        for (int base = 0; base < deg; base += 32) {
+            int c = 0;
+            float w = 0.f;
+            if (base + lane < deg) {
+                c = ld_stream_s32(a.idx + begin + base + lane);
+                w = ld_stream_f32(a.val + begin + base + lane);
+            }
+            const int n = min(32, deg - base);
+            for (int t = 0; t < n; ++t) {
+                const int ct = __shfl_sync(kFull, c, t);
+                const float wt = __shfl_sync(kFull, w, t);
+                if (col < K) acc = fmaf(__ldg(a.vin + (size_t)ct * K + col), wt, acc);
+            }
+        }
+        if (col < K) a.vout[(size_t)row * K + col] = acc;
+    }
+}
+
+// ---- heavy rows ----------------------------------------------------------------------------
+
+template <int LANES, int VEC>
+__global__ void __launch_bounds__(256) spmm_heavy_kernel(const RunArgs a) {
+    constexpr int GROUPS = 32 / LANES;
+    constexpr int U = (VEC == 1) ? 8 : 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int l = lane % LANES;
+    const int g = lane / LANES;
+    const int nwarps = blockDim.x >> 5;
+    int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) +
+                     warp * kStages;
+
+    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    const int slice = (int)(gw / a.n_seg);
+    if (slice >= a.n_slices) return;
+    const int seg = (int)(gw - (long long)slice * a.n_seg);
+    const SegDesc d = a.seg_desc[seg];
+    const int nchunks = (d.len + kChunk - 1) / kChunk;
+    const int2 *src = a.panel + d.panel_off;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int k) {
+        const int s = k % kStages;
+        const int n = min(kChunk, d.len - k * kChunk);
+        const uint32_t bytes = (uint32_t)((n + 1) & ~1) * 8u;   // panel is padded to 16 B
+        mbar_expect_tx(&bars[s], bytes);
+        tma_bulk_g2s(buf + s * kChunk, src + (size_t)k * kChunk, bytes, &bars[s]);
+    };
+    if (lane == 0) {
+        issue(0);
+        if (nchunks > 1) issue(1);
+    }
+
+    const int K = a.feat;
+    const int col0 = slice * a.kslice + l * 4;
+    const int col_end = min(K, (slice + 1) * a.kslice);
+    const float *bbase = a.vin + col0;
+    float4 acc[VEC];
+    bool colok[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        colok[v] = col0 + v * LANES * 4 < col_end;
+    }
+
+    for (int k = 0; k < nchunks; ++k) {
+        const int s = k % kStages;
+        mbar_wait(&bars[s], (uint32_t)(k / kStages) & 1u);
+        const int n = min(kChunk, d.len - k * kChunk);
+        const int2 *e = buf + s * kChunk;
+        for (int t0 = 0; t0 < n; t0 += GROUPS * U) {
+            float4 b[U][VEC];
+            float wt[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u * GROUPS + g;
+                ok[u] = t < n;
+                int2 cv = make_int2(0, 0);
+                if (ok[u]) cv = e[t];
+                wt[u] = __int_as_float(cv.y);
+                const float *brow = bbase + (size_t)cv.x * K;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (ok[u] && colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (ok[u] && colok[v]) fma4(acc[v], b[u][v], wt[u]);
+            }
+        }
+        __syncwarp();   // every lane is done reading stage s before it is refilled
+        if (lane == 0 && k + kStages < nchunks) issue(k + kStages);
+    }
+
+    // combine the lane groups (fixed tree => deterministic)
+#pragma unroll
+    for (int off = LANES; off < 32; off <<= 1) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            acc[v].x += __shfl_xor_sync(kFull, acc[v].x, off);
+            acc[v].y += __shfl_xor_sync(kFull, acc[v].y, off);
+            acc[v].z += __shfl_xor_sync(kFull, acc[v].z, off);
+            acc[v].w += __shfl_xor_sync(kFull, acc[v].w, off);
+        }
+    }
+    if (g == 0) {
+        float *prow = a.part + (size_t)seg * K + col0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (colok[v]) *reinterpret_cast<float4 *>(prow + v * LANES * 4) = acc[v];
+    }
+}
+
+// one thread per (heavy row, float4 column): partials added in segment order
+__global__ void __launch_bounds__(256) spmm_fixup_kernel(const RunArgs a) {
+    const int k4 = a.feat >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)a.n_heavy * k4) return;
+    const int hrow = (int)(t / k4);
+    const int c4 = (int)(t - (long long)hrow * k4);
+    const int s0 = a.heavy_seg0[hrow], s1 = a.heavy_seg0[hrow + 1];
+    const float4 *p = reinterpret_cast<const float4 *>(a.part) + (size_t)s0 * k4 + c4;
+    float4 acc = *p;
+    for (int s = s0 + 1; s < s1; ++s) {
+        p += k4;
+        const float4 x = *p;
+        acc.x += x.x;
+        acc.y += x.y;
+        acc.z += x.z;
+        acc.w += x.w;
+    }
+    st_c_row(a.vout + (size_t)a.heavy_rows[hrow] * a.feat + c4 * 4, acc);
+}
+
+// ---- preprocessing / support kernels ---------------------------------------------------------
+
+// one warp per segment: gather its {col, val} pairs into the panel, zero the pad entry
+__global__ void __launch_bounds__(256) build_panel_kernel(const SegDesc *seg, int n_seg, const int *idx,
+                                                          const float *val, int2 *panel) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_seg) return;
+    const SegDesc d = seg[gw];
+    const int padded = (d.len + 1) & ~1;
+    for (int t = lane; t < padded; t += 32) {
+        int2 e = make_int2(0, 0);
+        if (t < d.len) e = make_int2(idx[d.nnz_begin + t], __float_as_int(val[d.nnz_begin + t]));
+        panel[(size_t)d.panel_off + t] = e;
+    }
+}
+
+// splitmix64 finaliser; fill = Irwin-Hall(8 x 16 bit) scaled — see oracle/spmm_oracle.c
+// (oracle_fill_normal) for the definition both sides implement.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ int sum16x4(uint64_t a) {
+    return (int)(a & 0xFFFF) + (int)((a >> 16) & 0xFFFF) + (int)((a >> 32) & 0xFFFF) + (int)(a >> 48);
+}
+__global__ void __launch_bounds__(256) fill_normal_kernel(float *dst, long long n, uint64_t key, float scale,
+                                                          float mean) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t x = mix64(key + 2ull * (uint64_t)i);
+        const uint64_t y = mix64(key + 2ull * (uint64_t)i + 1ull);
+        const int t = sum16x4(x) + sum16x4(y) - 262140;
+        dst[i] = __fadd_rn(__fmul_rn((float)t, scale), mean);   // separate mul and add, as the oracle
+    }
+}
+
+// validate_float (PA4/handout/src/valid.cu:3-13) with an IEEE divide and a 64-bit counter
+__global__ void __launch_bounds__(256) valid_kernel(const float *y, const float *y2, long long num,
+                                                    unsigned long long *count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned int local = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < num; i += stride) {
+        const float q = __fdiv_rn(y[i] - y2[i], y[i]);
+        if ((double)fabsf(q) > 1e-2) ++local;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(kFull, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+
+template <int LANES, int VEC>
+int launch_shape(const RunArgs &a, int block, cudaStream_t stream, int *launches) {
+    const int warps = block / 32;
+    if (a.n_seg > 0) {
+        const long long tasks = (long long)a.n_seg * a.n_slices;
+        const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
+        spmm_heavy_kernel<LANES, VEC><<<(unsigned)((tasks + warps - 1) / warps), block, smem, stream>>>(a);
+        ++*launches;
+    }
+    if (a.n_light > 0) {
+        const long long tasks = (long long)a.light_tasks_per_slice * a.n_slices;
+        spmm_light_kernel<LANES, VEC><<<(unsigned)((tasks + warps - 1) / warps), block, 0, stream>>>(a);
+        ++*launches;
+    }
+    if (a.n_heavy > 0) {
+        const long long threads = (long long)a.n_heavy * (a.feat >> 2);
+        spmm_fixup_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a);
+        ++*launches;
+    }
+    return 0;
+}
+
+}  // namespace
+
+int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
+                int *launches) {
+    const Plan &p = h->plan;
+    RunArgs a;
+    a.ptr = h->d_ptr;
+    a.idx = h->d_idx;
+    a.val = h->d_val;
+    a.vin = vin;
+    a.vout = vout;
+    a.num_v = h->num_v;
+    a.feat = h->feat;
+    a.kslice = p.kslice;
+    a.n_slices = p.n_slices;
+    a.row_perm = p.d_row_perm;
+    a.n_light = p.n_light;
+    a.seg_desc = p.d_seg_desc;
+    a.panel = p.d_panel;
+    a.part = p.d_part;
+    a.n_seg = p.n_seg;
+    a.heavy_rows = p.d_heavy_rows;
+    a.heavy_seg0 = p.d_heavy_seg0;
+    a.n_heavy = p.n_heavy;
+    *launches = 0;
+    if (h->num_v == 0 || h->feat == 0) return 0;
+    if (p.scalar) {
+        a.light_tasks_per_slice = a.n_light;
+        const int warps = p.block / 32;
+        spmm_scalar_kernel<<<(unsigned)((a.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
+        ++*launches;
+    } else {
+        const int groups = 32 / p.lanes;
+        a.light_tasks_per_slice = (a.n_light + groups - 1) / groups;
+        switch (p.lanes * 10 + p.vec) {
+            case 11: launch_shape<1, 1>(a, p.block, stream, launches); break;
+            case 21: launch_shape<2, 1>(a, p.block, stream, launches); break;
+            case 41: launch_shape<4, 1>(a, p.block, stream, launches); break;
+            case 81: launch_shape<8, 1>(a, p.block, stream, launches); break;
+            case 161: launch_shape<16, 1>(a, p.block, stream, launches); break;
+            case 321: launch_shape<32, 1>(a, p.block, stream, launches); break;
+            case 322: launch_shape<32, 2>(a, p.block, stream, launches); break;
+            default:
+                set_error("unsupported kernel shape lanes=%d vec=%d", p.lanes, p.vec);
+                return SPMM_B200_EINVAL;
+        }
+    }
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_build_panel(const SegDesc *d_seg, int n_seg, const int *d_idx, const float *d_val,
+                       int2 *d_panel, cudaStream_t stream) {
+    if (n_seg == 0) return 0;
+    const long long threads = (long long)n_seg * 32;
+    build_panel_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_seg, n_seg, d_idx, d_val,
+                                                                             d_panel);
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream_id, float mean,
+                       float stddev, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    // host copy of mix64 for the key
+    auto hmix = [](uint64_t z) {
+        z += 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    const uint64_t key = hmix(seed ^ hmix(stream_id * 0x632BE59BD9B4E019ull + 0x1234567ull));
+    const float scale = (float)((double)stddev / 53510.0);
+    const long long blocks = (n + 255) / 256;
+    fill_normal_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(d_dst, n, key,
+                                                                                              scale, mean);
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_valid(const float *d_y, const float *d_y2, long long num, unsigned long long *d_count,
+                 cudaStream_t stream) {
+    if (num <= 0) return 0;
+    const long long blocks = (num + 255) / 256;
+    valid_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(d_y, d_y2, num,
+                                                                                         d_count);
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace spmm_b200

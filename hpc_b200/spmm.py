@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's SpMM operator interface.
+
+  struct CSR            PA4/handout/include/util.h:120-129   -> class CSR
+  class SpMM            PA4/handout/include/spmm_base.h:8-46 -> class SpMM
+  class SpMMOpt         PA4/handout/include/spmm_opt.h:5-26  -> class SpMMB200 (the slot it fills)
+  allocate<float>       PA4/handout/include/data.h:24-37     -> allocate / fill_normal
+  valid(float*,float*)  PA4/handout/src/valid.cu:41-56       -> valid
+
+Same names, argument meaning and call protocol (preprocess once, then run any number of
+times; run is asynchronous on the current stream and the caller synchronises). All tensors
+are CUDA tensors; only their data pointers cross the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from ._lib import PlanInfo, check, lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class CSR:
+    """struct CSR: device pointers, int32 indices (util.h:120-129)."""
+
+    num_v: int
+    num_e: int
+    ptr: torch.Tensor  # int32[num_v + 1]
+    idx: torch.Tensor  # int32[num_e]
+    val: torch.Tensor  # float32[num_e]
+
+    def __post_init__(self):
+        for name, t, dt, n in (("ptr", self.ptr, torch.int32, self.num_v + 1),
+                               ("idx", self.idx, torch.int32, self.num_e),
+                               ("val", self.val, torch.float32, self.num_e)):
+            if not t.is_cuda or t.dtype != dt or not t.is_contiguous() or t.numel() < n:
+                raise ValueError(f"CSR.{name}: need a contiguous CUDA {dt} tensor of >= {n} elements")
+
+
+class SpMM:
+    """class SpMM (spmm_base.h:8-46): abstract operator over a borrowed CSR."""
+
+    def __init__(self, g: CSR, feat_in: int):
+        self.g = g
+        self.num_v, self.num_e, self.feat_in = g.num_v, g.num_e, int(feat_in)
+
+    def set_feat(self, feat_in: int) -> None:
+        self.feat_in = int(feat_in)
+
+    def preprocess(self, vin, vout) -> None:
+        raise NotImplementedError
+
+    def run(self, vin, vout) -> None:
+        raise NotImplementedError
+
+
+class SpMMB200(SpMM):
+    """The engine, in the slot of SpMMOpt (PA4/handout/src/spmm_opt.cu:3-11)."""
+
+    def __init__(self, g: CSR, feat_in: int, **options):
+        super().__init__(g, feat_in)
+        h = C.c_void_p()
+        check(lib.spmm_b200_create(_ptr(g.ptr), _ptr(g.idx), _ptr(g.val), g.num_v, g.num_e,
+                                   self.feat_in, C.byref(h)))
+        self._h = h
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def set_option(self, name: str, value: int) -> None:
+        check(lib.spmm_b200_set_option(self._h, name.encode(), int(value)))
+
+    def set_feat(self, feat_in: int) -> None:
+        super().set_feat(feat_in)
+        check(lib.spmm_b200_set_feat(self._h, self.feat_in))
+
+    def _check_io(self, vin, vout):
+        n = self.num_v * self.feat_in
+        for name, t in (("vin", vin), ("vout", vout)):
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
+                raise ValueError(f"{name}: need a contiguous CUDA float32 tensor of >= {n} elements")
+
+    def preprocess(self, vin, vout) -> None:
+        self._check_io(vin, vout)
+        check(lib.spmm_b200_preprocess(self._h, _ptr(vin), _ptr(vout), _stream()))
+
+    def run(self, vin, vout) -> None:
+        self._check_io(vin, vout)
+        check(lib.spmm_b200_run(self._h, _ptr(vin), _ptr(vout), _stream()))
+
+    def run_host(self, h_vin: torch.Tensor, h_vout: torch.Tensor) -> None:
+        """H2D(vin) -> run -> D2H(vout) -> sync, host (ideally pinned) float32 tensors."""
+        n = self.num_v * self.feat_in
+        for name, t in (("h_vin", h_vin), ("h_vout", h_vout)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
+                raise ValueError(f"{name}: need a contiguous host float32 tensor of >= {n} elements")
+        check(lib.spmm_b200_run_host(self._h, C.c_void_p(h_vin.data_ptr()), C.c_void_p(h_vout.data_ptr()),
+                                     _stream()))
+
+    @property
+    def launches_per_run(self) -> int:
+        return lib.spmm_b200_launches_per_run(self._h)
+
+    def plan_info(self) -> dict:
+        info = PlanInfo()
+        check(lib.spmm_b200_plan_info(self._h, C.byref(info)))
+        return info.as_dict()
+
+    def plan_arrays(self) -> dict:
+        """The plan, copied to host numpy arrays (parity tests compare these with the oracle)."""
+        info = self.plan_info()
+        out = {}
+        for which, name, n in ((0, "row_perm", info["n_light"]), (1, "heavy_rows", info["n_heavy"]),
+                               (2, "heavy_seg0", info["n_heavy"] + 1 if info["n_heavy"] else 0),
+                               (3, "seg_desc", info["n_seg"] * 4), (4, "panel", info["panel_len"] * 2)):
+            a = np.empty(n, dtype=np.int32)
+            check(lib.spmm_b200_plan_copy(self._h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
+            out[name] = a
+        out["seg_desc"] = out["seg_desc"].reshape(-1, 4)
+        out["panel"] = out["panel"].reshape(-1, 2)
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.spmm_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def fill_normal(t: torch.Tensor, seed: int, stream_id: int, mean: float = 0.0, stddev: float = 0.1) -> torch.Tensor:
+    """Counter-based N(mean, stddev) fill (the engine's stand-in for curandGenerateNormal, data.h:31)."""
+    if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError("fill_normal: need a contiguous CUDA float32 tensor")
+    check(lib.spmm_b200_fill_normal(_ptr(t), t.numel(), seed, stream_id, mean, stddev, _stream()))
+    return t
+
+
+_alloc_counter = [0]
+
+
+def allocate(num: int, seed: int = 123, random: bool = True, device="cuda") -> torch.Tensor:
+    """allocate<float>(num) (data.h:24-37): rounded up to 512 elements, N(0, 0.1)-filled.
+    Successive calls draw from successive streams, as successive curand calls do."""
+    t = torch.empty((num + 511) // 512 * 512, dtype=torch.float32, device=device)
+    if random:
+        fill_normal(t, seed, _alloc_counter[0])
+        _alloc_counter[0] += 1
+    return t
+
+
+def valid(y: torch.Tensor, y2: torch.Tensor, num: int) -> int:
+    """valid(y, y2, num) (valid.cu:41-56): count of |(y - y2) / y| > 1e-2."""
+    out = C.c_longlong(0)
+    check(lib.spmm_b200_valid(_ptr(y), _ptr(y2), num, C.byref(out), _stream()))
+    return out.value
+
+
+def plan_host(ptr: np.ndarray, seg_len: int = 0, reorder: bool = True) -> dict:
+    """The row part of the plan from a host ptr array (spmm_b200_plan_host); no GPU needed."""
+    ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+    m = len(ptr) - 1
+    nl, nh, ns, pl = C.c_int(0), C.c_int(0), C.c_int(0), C.c_longlong(0)
+    args = (C.c_void_p(ptr.ctypes.data), m, int(seg_len), int(bool(reorder)))
+    check(lib.spmm_b200_plan_host(*args, None, C.byref(nl), None, C.byref(nh), None, None, C.byref(ns), C.byref(pl)))
+    row_perm = np.empty(nl.value, np.int32)
+    heavy_rows = np.empty(nh.value, np.int32)
+    heavy_seg0 = np.empty(nh.value + 1 if nh.value else 0, np.int32)
+    seg_desc = np.empty(ns.value * 4, np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    check(lib.spmm_b200_plan_host(*args, vp(row_perm), C.byref(nl), vp(heavy_rows), C.byref(nh), vp(heavy_seg0),
+                                  vp(seg_desc), C.byref(ns), C.byref(pl)))
+    return {"row_perm": row_perm, "heavy_rows": heavy_rows, "heavy_seg0": heavy_seg0,
+            "seg_desc": seg_desc.reshape(-1, 4), "panel_len": pl.value}

@@ -1,0 +1,166 @@
+/*
+ * spmm_b200.h — C ABI of the B200-native CSR SpMM engine (C = A·B, A sparse CSR fp32,
+ * B/C dense row-major fp32 with leading dimension K).
+ *
+ * This header is the drop-in boundary for the SpMM operator of liblaf/hpc PA4. Every entry
+ * point cites the reference interface it replaces (paths relative to the reference root).
+ * Plain pointers and sizes only; no C++ / torch types. All functions return 0 on success or
+ * a non-zero status (a cudaError_t value when a CUDA call failed, a negative SPMM_B200_E*
+ * code otherwise) and never exit or throw; spmm_b200_last_error() gives the text.
+ *
+ * Ownership (PA4/handout/test/main.cpp:11-16, test/test_spmm.cu:16-28): ptr/idx/val/vin/vout
+ * are DEVICE pointers owned by the caller and borrowed for the handle's lifetime; everything
+ * preprocess allocates is owned by the handle and released by spmm_b200_destroy.
+ */
+#ifndef SPMM_B200_H_
+#define SPMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMM_B200_EINVAL (-1)   /* bad argument */
+#define SPMM_B200_ESTATE (-2)   /* call protocol violated (run before preprocess, ...) */
+#define SPMM_B200_EIO (-3)      /* graph file missing / malformed */
+#define SPMM_B200_ENOMEM (-4)   /* host allocation failed */
+
+typedef struct spmm_b200_handle *spmm_b200_t;
+
+/* ---- operator: class SpMM (PA4/handout/include/spmm_base.h:8-46) ------------------------- */
+
+/* SpMM::SpMM(CSR *g, int feat_in)  (spmm_base.h:14-21; struct CSR: include/util.h:120-129).
+ * d_ptr int32[num_v+1], d_idx int32[num_e], d_val f32[num_e]: device pointers. */
+int spmm_b200_create(const int *d_ptr, const int *d_idx, const float *d_val, int num_v, int num_e,
+                     int feat_in, spmm_b200_t *out);
+
+/* SpMM::set_feat (spmm_base.h:26-29). Invalidates the plan: preprocess must be called again. */
+int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
+
+/* Tunables, set before preprocess. Unknown names return SPMM_B200_EINVAL.
+ *   "seg_len"   nonzeros per heavy-row segment; rows longer than this are split (0 = auto)
+ *   "kslice"    feature columns per pass over the graph (0 = auto; else multiple of 4)
+ *   "block"     threads per CTA (multiple of 32)
+ *   "reorder"   1 = degree-bucketed row order (default), 0 = natural order
+ * The reference's counterpart are the compile-time constants kBatchSize / kTasksPerBlock
+ * (PA4/workspace/src/spmm_opt.cu:6-7). */
+int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value);
+
+/* SpMM::preprocess(float *vin, float *vout)  (spmm_base.h:31; student version
+ * PA4/workspace/src/spmm_opt.cu:37-69). Builds the plan: degree-bucketed row order, heavy-row
+ * segments, staged col/val panels. vin/vout are hints only and are not written (the student's
+ * preprocess zeroes vout, spmm_opt.cu:67-68; this engine's run overwrites vout instead).
+ * Runs on `stream` and synchronises it before returning. */
+int spmm_b200_preprocess(spmm_b200_t h, const float *vin, float *vout, void *stream);
+
+/* SpMM::run(float *vin, float *vout)  (spmm_base.h:32; PA4/handout/src/spmm_ref.cu:27-30).
+ * Asynchronous on `stream` (a cudaStream_t; NULL = the default stream, as in the reference).
+ * Fully overwrites vout[num_v*feat_in]; does not depend on its previous contents. */
+int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream);
+
+/* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). */
+int spmm_b200_destroy(spmm_b200_t h);
+
+/* Host-buffer convenience for callers that hold B and C on the host: H2D(vin) → run → D2H(vout)
+ * on `stream`, then synchronise. The handle keeps device staging buffers of num_v*feat_in floats.
+ * (The reference's harness keeps everything on the device; this is the end-to-end call that
+ * bench.py times as `e2e`.) */
+int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *stream);
+
+const char *spmm_b200_last_error(void);
+
+/* Number of kernels the last spmm_b200_run launched (for bench.py's gpu_launches). */
+int spmm_b200_launches_per_run(spmm_b200_t h);
+
+/* ---- plan introspection (parity tests: plan must equal the CPU oracle bit for bit) --------- */
+
+typedef struct {
+    int num_v, num_e, feat_in;
+    int seg_len;        /* effective nonzeros per segment */
+    int kslice;         /* effective feature columns per pass */
+    int n_slices;       /* ceil(feat_in / kslice) */
+    int block;          /* threads per CTA */
+    int n_light;        /* rows handled whole (row_perm length) */
+    int n_heavy;        /* rows split into segments */
+    int n_seg;          /* total segments */
+    long long panel_len; /* entries (8 bytes each) in the staged col/val panel */
+    int lanes;          /* lanes cooperating on one row in the light kernel */
+    int vec;            /* float4 per lane */
+} spmm_b200_plan_info_t;
+
+int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
+
+/* Copy one plan array to the host. which:
+ *   0 row_perm   int32[n_light]     light rows in processing order
+ *   1 heavy_rows int32[n_heavy]     heavy rows in processing order
+ *   2 heavy_seg0 int32[n_heavy+1]   first segment of each heavy row (prefix)
+ *   3 seg_desc   int32[n_seg*4]     {row, panel_off, len, nnz_begin} per segment
+ *   4 panel      int32[panel_len*2] {col, float bits of val} pairs, segment-major
+ * Returns SPMM_B200_EINVAL when `bytes` is not the exact size. */
+int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);
+
+/* The row part of the plan computed from a HOST ptr array, no GPU needed (the same routine
+ * preprocess uses after copying ptr to the host). Call once with the array arguments NULL to
+ * get the counts, then with row_perm int32[n_light], heavy_rows int32[n_heavy], heavy_seg0
+ * int32[n_heavy+1 (0 if none)], seg_desc int32[n_seg*4]. seg_len <= 0 selects the automatic
+ * value for nnz = h_ptr[num_v]. */
+int spmm_b200_plan_host(const int *h_ptr, int num_v, long long seg_len, int reorder, int *row_perm,
+                        int *n_light, int *heavy_rows, int *n_heavy, int *heavy_seg0, int *seg_desc,
+                        int *n_seg, long long *panel_len);
+
+/* ---- support (device pointers) ------------------------------------------------------------ */
+
+/* allocate<float>'s fill (PA4/handout/include/data.h:24-37: curandGenerateNormal(0, 0.1)):
+ * counter-based N(mean, stddev) fill, element i of (seed, stream_id) identical to the CPU
+ * oracle's generator. */
+int spmm_b200_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream_id, float mean,
+                          float stddev, void *stream);
+
+/* valid(float *y, float *y2, int num) (PA4/handout/src/valid.cu:3-13,41-56): number of elements
+ * with |(y - y2) / y| > 1e-2 (IEEE divide). Synchronises. */
+int spmm_b200_valid(const float *d_y, const float *d_y2, long long num, long long *mismatches,
+                    void *stream);
+
+/* ---- graphs (host pointers) ---------------------------------------------------------------- */
+
+/* Synthetic stand-in for the OGB/DGL graphs the reference loads from ~/PA4/data
+ * (PA4/handout/script/run_all.sh:11): power-law row degrees rescaled to exactly `nnz` with
+ * maximum `max_deg` (the per-graph figure PA4/workspace/phase_2.log pins), columns drawn from
+ * a popularity-skewed + local mixture, unique and ascending within a row.
+ *   tail_k      degree weight = u^(-tail_k/4), tail_k in 1..4 (Pareto alpha = 4/tail_k)
+ *   zero_ppm    fraction of empty rows, parts per million
+ *   local_ppm   fraction of a row's columns drawn from the window [r-window, r+window]
+ * ptr int32[num_v+1] and idx int32[nnz] are caller-allocated host arrays. */
+int spmm_b200_gen_graph(int num_v, long long nnz, int max_deg, int tail_k, int zero_ppm,
+                        int local_ppm, int window, uint64_t seed, int *ptr, int *idx);
+
+/* Degrees only (first half of the above), deg int32[num_v]. */
+int spmm_b200_gen_degrees(int num_v, long long nnz, int max_deg, int tail_k, int zero_ppm,
+                          uint64_t seed, int *deg);
+
+/* load_graph (PA4/handout/src/data.cu:3-66): <dir>/<dset>.config ("num_v num_e"),
+ * <dset>.graph (text: num_v+1 ptr ints then num_e idx ints), binary caches
+ * <dset>.graph.ptrdump / .edgedump (int32), written on first text read.
+ * Pass ptr = idx = NULL to query the sizes only. */
+int spmm_b200_load_graph(const char *datadir, const char *dset, int *num_v, int *num_e, int *ptr,
+                         int *idx);
+
+/* Writes <dset>.config plus either the text .graph (text != 0) or the two binary dumps. */
+int spmm_b200_write_graph(const char *datadir, const char *dset, int num_v, int num_e,
+                          const int *ptr, const int *idx, int text);
+
+/* ---- multi-GPU (no reference counterpart) ------------------------------------- */
+
+/* nnz-balanced contiguous row partition: bounds[g] = first row r with ptr[r] >= g*nnz/parts
+ * (64-bit arithmetic), bounds[0] = 0, bounds[parts] = num_v. h_ptr is a host array. */
+int spmm_b200_partition_rows(const int *h_ptr, int num_v, int parts, int *bounds);
+
+/* Rebase one partition: out_ptr[i] = h_ptr[row_begin + i] - h_ptr[row_begin], i in [0, rows]. */
+int spmm_b200_rebase_ptr(const int *h_ptr, int row_begin, int row_end, int *out_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMM_B200_H_ */

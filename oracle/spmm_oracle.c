@@ -1,0 +1,218 @@
+/*
+ * oracle/spmm_oracle.c — CPU restatement of the reference's CSR SpMM path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE. Only tests/, the smoke check in
+ * __graft_entry__.py and bench.py's cpu_baseline / `--impl reference` legs may load
+ * it. Nothing under hpc_b200/ links, imports or calls it; the product path fails
+ * loudly when its CUDA library is missing instead of falling back to this file.
+ *
+ * Parity status: the reference (liblaf/hpc PA4) ships no golden vector for SpMM
+ * (SURVEY.md §8c); this restatement is pinned against the reference's own kernel
+ * `spmm_kernel_ref` rebuilt from /root/reference for sm_100a (oracle/_ref, see
+ * oracle/Makefile) in tests/test_gpu_parity.py, bit for bit, and against the
+ * committed fixtures in tests/golden/ (made by tests/golden/make_golden.py).
+ *
+ * Each function cites the reference file:line (relative to /root/reference) it follows.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* FFMA.FTZ model. The handout builds with --use_fast_math (PA4/handout/CMakeLists.txt:46),
+ * so `result += vin[..] * val[i]` (PA4/handout/src/spmm_ref.cu:13) is one FFMA.FTZ:
+ * subnormal inputs are read as signed zero and a subnormal result is written as signed zero. */
+static inline float ftz1(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0) { u &= 0x80000000u; memcpy(&x, &u, 4); }
+    return x;
+}
+static inline float ffma_ftz(float a, float b, float c) {
+    return ftz1(fmaf(ftz1(a), ftz1(b), ftz1(c)));
+}
+
+/*
+ * PA4/handout/src/spmm_ref.cu:3-17 (spmm_kernel_ref), literal loop order:
+ * one "thread" per row, j outer, i inner, accumulator starts at 0.0f, in-order FMA chain.
+ * The reference indexes vin with `idx[i] * INFEATURE + j` in 32-bit int; the sizes used
+ * here never overflow that, and the restatement uses size_t.
+ */
+void oracle_spmm_literal(const int *ptr, const int *idx, const float *val, const float *vin,
+                         float *vout, int num_v, int feat, int ftz) {
+    for (int tid = 0; tid < num_v; ++tid) {
+        int begin = ptr[tid], end = ptr[tid + 1];
+        for (int j = 0; j < feat; ++j) {
+            float result = 0.0f;
+            for (int i = begin; i < end; ++i) {
+                float b = vin[(size_t)idx[i] * feat + j];
+                result = ftz ? ffma_ftz(b, val[i], result) : fmaf(b, val[i], result);
+            }
+            vout[(size_t)tid * feat + j] = result;
+        }
+    }
+}
+
+/*
+ * Same arithmetic as spmm_ref.cu:7-16 with the two inner loops interchanged (i outer,
+ * j inner) so the compiler can vectorise over j. Every output element still sees the
+ * identical in-order FMA chain from 0.0f, so the result is bit-identical to the literal
+ * order (tests/test_oracle.py checks memcmp equality). Rows [row_begin, row_end) only,
+ * so bench.py can time a bounded sample; OpenMP over rows, dynamic schedule because the
+ * degree distribution is heavy-tailed.
+ */
+void oracle_spmm_f32(const int *ptr, const int *idx, const float *val, const float *vin,
+                     float *vout, int feat, int row_begin, int row_end, int ftz, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        float *acc = (float *)malloc(sizeof(float) * (size_t)(feat > 0 ? feat : 1));
+#pragma omp for schedule(dynamic, 16)
+        for (int r = row_begin; r < row_end; ++r) {
+            for (int j = 0; j < feat; ++j) acc[j] = 0.0f;
+            for (int i = ptr[r]; i < ptr[r + 1]; ++i) {
+                const float v = val[i];
+                const float *b = vin + (size_t)idx[i] * feat;
+                if (ftz) {
+                    for (int j = 0; j < feat; ++j) acc[j] = ffma_ftz(b[j], v, acc[j]);
+                } else {
+                    for (int j = 0; j < feat; ++j) acc[j] = fmaf(b[j], v, acc[j]);
+                }
+            }
+            memcpy(vout + (size_t)r * feat, acc, sizeof(float) * (size_t)feat);
+        }
+        free(acc);
+    }
+}
+
+/* fp64 accumulation of the same sum (error budgeting only; no reference counterpart). */
+void oracle_spmm_f64(const int *ptr, const int *idx, const float *val, const float *vin,
+                     double *vout, int feat, int row_begin, int row_end, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int r = row_begin; r < row_end; ++r) {
+        double *o = vout + (size_t)r * feat;
+        for (int j = 0; j < feat; ++j) o[j] = 0.0;
+        for (int i = ptr[r]; i < ptr[r + 1]; ++i) {
+            const double v = (double)val[i];
+            const float *b = vin + (size_t)idx[i] * feat;
+            for (int j = 0; j < feat; ++j) o[j] += (double)b[j] * v;
+        }
+    }
+}
+
+/*
+ * Sum of |b*v| per output element in fp64: the scale against which a split-row
+ * (re-associated) result is allowed to differ. Test infrastructure only.
+ */
+void oracle_spmm_abssum(const int *ptr, const int *idx, const float *val, const float *vin,
+                        double *vout, int feat, int row_begin, int row_end) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int r = row_begin; r < row_end; ++r) {
+        double *o = vout + (size_t)r * feat;
+        for (int j = 0; j < feat; ++j) o[j] = 0.0;
+        for (int i = ptr[r]; i < ptr[r + 1]; ++i) {
+            const double v = fabs((double)val[i]);
+            const float *b = vin + (size_t)idx[i] * feat;
+            for (int j = 0; j < feat; ++j) o[j] += fabs((double)b[j]) * v;
+        }
+    }
+}
+
+/*
+ * PA4/handout/src/valid.cu:3-13 (validate_float) + :41-56 (valid): number of elements with
+ * |(ref[t]-ans[t])/ref[t]| > 1e-2. The first argument is the one that normalises; the
+ * handout's test passes the CANDIDATE there (PA4/handout/test/test_spmm.cu:43).
+ * 0/0 = NaN is not counted, x/0 = inf is counted. The handout's divide is the fast-math
+ * approximate one; this uses IEEE division (differs only for ratios within 2 ulp of 1e-2).
+ */
+long long oracle_validate_float(const float *ref, const float *ans, long long num) {
+    long long diff = 0;
+#pragma omp parallel for reduction(+ : diff)
+    for (long long t = 0; t < num; ++t) {
+        float q = (ref[t] - ans[t]) / ref[t];
+        if ((double)fabsf(q) > 1e-2) diff += 1;
+    }
+    return diff;
+}
+
+/* PA4/handout/src/valid.cu:15-25 (validate_int): exact mismatch count. */
+long long oracle_validate_int(const int *ref, const int *ans, long long num) {
+    long long diff = 0;
+    for (long long t = 0; t < num; ++t) diff += (ref[t] != ans[t]);
+    return diff;
+}
+
+/*
+ * Input values. The handout fills vin/vout/val with curandGenerateNormal(mean 0, stddev 0.1)
+ * from an XORWOW generator seeded 123 (PA4/handout/include/data.h:24-37, test/main.cpp:19-20).
+ * cuRAND's stream cannot be reproduced on the CPU, so both sides use this counter-based
+ * generator instead: element i of stream `stream` under `seed` is
+ *     t = (sum of the eight 16-bit fields of two splitmix64 outputs) - 262140
+ *     x = (float)t * (float)(stddev / 53510.0) + mean
+ * (Irwin–Hall with n = 8: mean 0, variance 8*(65536^2-1)/12, i.e. sigma 53510.09; support
+ * ±4.9 sigma.) Integer arithmetic plus one correctly-rounded float multiply and add, so CPU,
+ * numpy and the CUDA fill kernel agree bit for bit.
+ */
+static inline uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline int sum16x4(uint64_t a) {
+    return (int)(a & 0xFFFF) + (int)((a >> 16) & 0xFFFF) + (int)((a >> 32) & 0xFFFF) + (int)(a >> 48);
+}
+void oracle_fill_normal(float *dst, long long n, uint64_t seed, uint64_t stream, float mean, float stddev) {
+    const uint64_t key = mix64(seed ^ mix64(stream * 0x632BE59BD9B4E019ull + 0x1234567ull));
+    const float scale = (float)((double)stddev / 53510.0);
+#pragma omp parallel for
+    for (long long i = 0; i < n; ++i) {
+        uint64_t a = mix64(key + 2ull * (uint64_t)i);
+        uint64_t b = mix64(key + 2ull * (uint64_t)i + 1ull);
+        int t = sum16x4(a) + sum16x4(b) - 262140;
+        volatile float p = (float)t * scale; /* volatile: keep mul and add separate (no FMA contraction) */
+        dst[i] = p + mean;
+    }
+}
+
+/*
+ * PA4/workspace/src/spmm_opt.cu:43-54 (student's SpMMOpt::preprocess, BEFORE the unseeded
+ * std::random_shuffle at :57): every row cut into Task{row, ptr_begin, ptr_end} of at most
+ * `batch` (=256, :6) nonzeros, rows with no nonzeros emit nothing. Returns the task count;
+ * writes 3 ints per task when `tasks` is not NULL. Cross-check for the segment splitter.
+ */
+long long oracle_student_tasks(const int *ptr, int num_v, int batch, int *tasks) {
+    long long n = 0;
+    for (int row = 0; row < num_v; ++row) {
+        const int begin = ptr[row], end = ptr[row + 1];
+        for (int b = begin; b < end; b += batch) {
+            if (tasks) {
+                tasks[3 * n + 0] = row;
+                tasks[3 * n + 1] = b;
+                tasks[3 * n + 2] = (b + batch < end) ? b + batch : end;
+            }
+            ++n;
+        }
+    }
+    return n;
+}
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,51 @@
+"""The C-ABI library loads and exports every symbol include/spmm_b200.h declares (no GPU work)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "spmm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spmm_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    names = _declared()
+    assert len(names) >= 18
+    lib = ctypes.CDLL(os.path.join(ROOT, "hpc_b200", "libspmm_b200.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header():
+    from hpc_b200._lib import SIGNATURES
+    assert sorted(SIGNATURES) == _declared()
+
+
+def test_status_codes_without_gpu():
+    """Argument errors are reported as codes + message, never exit() (reference aborts: util.h:63-84)."""
+    import hpc_b200
+    from hpc_b200._lib import lib
+    h = ctypes.c_void_p()
+    rc = lib.spmm_b200_create(None, None, None, 5, 0, 32, ctypes.byref(h))   # num_v > 0 with NULL ptr
+    assert rc == -1 and b"bad arguments" in lib.spmm_b200_last_error()
+    assert lib.spmm_b200_create(None, None, None, 0, 0, 32, ctypes.byref(h)) == 0
+    assert lib.spmm_b200_set_option(h, b"nonsense", 1) == -1
+    assert lib.spmm_b200_set_option(h, b"kslice", 6) == -1          # not a multiple of 4
+    assert lib.spmm_b200_run(h, None, None, None) == -2             # run before preprocess
+    assert b"preprocess" in lib.spmm_b200_last_error()
+    assert lib.spmm_b200_destroy(h) == 0
+
+
+def test_product_does_not_import_oracle():
+    """The product package never references oracle/ (no CPU fallback on the product path)."""
+    pkg = os.path.join(ROOT, "hpc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "oracle/_ref" not in text, f
