@@ -38,13 +38,14 @@ SIGNATURES = {
     "spmm_b200_set_option": (_I, [_P, C.c_char_p, _LL]),
     "spmm_b200_preprocess": (_I, [_P, _P, _P, _P]),
     "spmm_b200_run": (_I, [_P, _P, _P, _P]),
+    "spmm_b200_run_profiled": (_I, [_P, _P, _P, _P, C.POINTER(C.c_float)]),
     "spmm_b200_destroy": (_I, [_P]),
     "spmm_b200_run_host": (_I, [_P, _P, _P, _P]),
     "spmm_b200_last_error": (C.c_char_p, []),
     "spmm_b200_launches_per_run": (_I, [_P]),
     "spmm_b200_plan_info": (_I, [_P, C.POINTER(PlanInfo)]),
     "spmm_b200_plan_copy": (_I, [_P, _I, _P, C.c_size_t]),
-    "spmm_b200_plan_host": (_I, [_P, _I, _LL, _I, _P, C.POINTER(_I), _P, C.POINTER(_I), _P, _P, C.POINTER(_I),
+    "spmm_b200_plan_host": (_I, [_P, _I, _I, _LL, _I, _P, C.POINTER(_I), _P, C.POINTER(_I), _P, _P, C.POINTER(_I),
                                  C.POINTER(_LL)]),
     "spmm_b200_fill_normal": (_I, [_P, _LL, _U64, _U64, C.c_float, C.c_float, _P]),
     "spmm_b200_valid": (_I, [_P, _P, _LL, C.POINTER(_LL), _P]),

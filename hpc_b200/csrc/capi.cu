@@ -73,6 +73,11 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     else if (!strcmp(name, "kslice") && value >= 0 && value % 4 == 0) h->opt_kslice = value;
     else if (!strcmp(name, "block") && value >= 32 && value <= 256 && value % 32 == 0) h->opt_block = value;
     else if (!strcmp(name, "reorder") && (value == 0 || value == 1)) h->opt_reorder = value;
+    else if (!strcmp(name, "tune") && value >= 0 && value <= 3) h->opt_tune = value;
+    else if (!strcmp(name, "b_rows") && value >= 0 && value <= 0x7fffffffll) {
+        h->b_rows = (int)value;   // does not touch the plan
+        return 0;
+    }
     else {
         set_error("spmm_b200_set_option: unknown option or bad value: %s = %lld", name, value);
         return SPMM_B200_EINVAL;
@@ -111,6 +116,29 @@ int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream) {
     return launch_spmm(h, vin, vout, (cudaStream_t)stream, &h->plan.launches);
 }
 
+int spmm_b200_run_profiled(spmm_b200_t h, const float *vin, float *vout, void *stream, float *ms) {
+    if (!h || !ms) {
+        set_error("spmm_b200_run_profiled: null argument");
+        return SPMM_B200_EINVAL;
+    }
+    if (!h->plan.ready) {
+        set_error("spmm_b200_run_profiled: preprocess has not been called");
+        return SPMM_B200_ESTATE;
+    }
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) SB_CUDA(cudaEventCreate(&ev[i]));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaEventRecord(ev[0], s);
+    int rc = launch_spmm(h, vin, vout, s, &h->plan.launches);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[1], s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ev[1]);
+    if (rc == 0 && e == cudaSuccess) e = cudaEventElapsedTime(ms, ev[0], ev[1]);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(ev[i]);
+    if (rc) return rc;
+    SB_CUDA(e);
+    return 0;
+}
+
 int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *stream) {
     if (!h || !h_vin || !h_vout) {
         set_error("spmm_b200_run_host: null argument");
@@ -121,18 +149,20 @@ int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *s
         return SPMM_B200_ESTATE;
     }
     const size_t n = (size_t)h->num_v * h->feat;
+    const size_t nb = (size_t)(h->b_rows > 0 ? h->b_rows : h->num_v) * h->feat;
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->stage_elems < n) {
+    if (h->stage_elems < n || h->stage_in_elems < nb) {
         cudaFree(h->d_stage_in);
         cudaFree(h->d_stage_out);
         h->d_stage_in = h->d_stage_out = nullptr;
-        h->stage_elems = 0;
-        SB_CUDA(cudaMalloc((void **)&h->d_stage_in, n * sizeof(float)));
+        h->stage_elems = h->stage_in_elems = 0;
+        SB_CUDA(cudaMalloc((void **)&h->d_stage_in, nb * sizeof(float)));
         SB_CUDA(cudaMalloc((void **)&h->d_stage_out, n * sizeof(float)));
         h->stage_elems = n;
+        h->stage_in_elems = nb;
     }
-    SB_CUDA(cudaMemcpyAsync(h->d_stage_in, h_vin, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_stage_in, h_vin, nb * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = launch_spmm(h, h->d_stage_in, h->d_stage_out, s, &h->plan.launches);
     if (rc) return rc;
     SB_CUDA(cudaMemcpyAsync(h_vout, h->d_stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -187,6 +217,8 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
         case 2: src = p.d_heavy_seg0; want = p.n_heavy ? sizeof(int) * ((size_t)p.n_heavy + 1) : 0; break;
         case 3: src = p.d_seg_desc; want = sizeof(SegDesc) * (size_t)p.n_seg; break;
         case 4: src = p.d_panel; want = sizeof(int2) * (size_t)p.panel_len; break;
+        case 5: src = p.d_light_desc; want = sizeof(int4) * (size_t)p.n_light; break;
+        case 6: src = p.d_seg_hrow; want = sizeof(int) * (size_t)p.n_seg; break;
         default: set_error("spmm_b200_plan_copy: unknown array %d", which); return SPMM_B200_EINVAL;
     }
     if (bytes != want) {
@@ -194,12 +226,7 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
         return SPMM_B200_EINVAL;
     }
     if (want == 0) return 0;
-    if (!src) {   // natural order: row_perm is implicit
-        if (which == 0) {
-            int *dst = (int *)host_dst;
-            for (int i = 0; i < p.n_light; ++i) dst[i] = i;
-            return 0;
-        }
+    if (!src) {
         set_error("spmm_b200_plan_copy: array %d is empty", which);
         return SPMM_B200_ESTATE;
     }

@@ -29,41 +29,43 @@ struct SegDesc {
     int nnz_begin;
 };
 
-// Everything a run needs, passed to the kernels by value.
+// Everything a run needs, passed to the kernel by value.
 struct RunArgs {
-    const int *ptr;
     const int *idx;
     const float *val;
     const float *vin;
     float *vout;
-    int num_v;
     int feat;        // K
     int kslice;      // feature columns per pass
     int n_slices;
     // light rows
-    const int *row_perm;   // NULL = natural order
+    const int4 *light_desc;   // {row, begin, deg, 0} in processing order
     int n_light;
     int light_tasks_per_slice;   // warps per slice
     // heavy rows
     const SegDesc *seg_desc;
+    const int *seg_hrow;       // segment -> index of its row in heavy_rows
+    const int *heavy_seg0;     // heavy row -> first segment (prefix, n_heavy + 1)
+    int *seg_count;            // [n_heavy][n_slices] finished-segment counters, zero between runs
     const int2 *panel;
-    float *part;           // [n_seg][K] partial sums
+    float *part;               // [n_seg][K] partial sums
     int n_seg;
-    const int *heavy_rows;
-    const int *heavy_seg0;
-    int n_heavy;
+    long long heavy_tasks;     // n_seg * n_slices
 };
 
 struct Plan {
     bool ready = false;
-    int seg_len = 0, kslice = 0, n_slices = 0, block = 256, lanes = 0, vec = 0;
+    int seg_len = 0, kslice = 0, n_slices = 0, block = 256, lanes = 0, vec = 0, tune = 0;
     bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
     int n_light = 0, n_heavy = 0, n_seg = 0;
     long long panel_len = 0;
     int *d_row_perm = nullptr;
+    int4 *d_light_desc = nullptr;
     int *d_heavy_rows = nullptr;
     int *d_heavy_seg0 = nullptr;
     SegDesc *d_seg_desc = nullptr;
+    int *d_seg_hrow = nullptr;
+    int *d_seg_count = nullptr;
     int2 *d_panel = nullptr;
     float *d_part = nullptr;
     int launches = 0;
@@ -76,10 +78,11 @@ struct spmm_b200_handle {
     const int *d_idx = nullptr;
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
-    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 256, opt_reorder = 1;
+    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 256, opt_reorder = 1, opt_tune = 0;
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
-    size_t stage_elems = 0;
+    size_t stage_elems = 0, stage_in_elems = 0;
+    int b_rows = 0;   // rows of B (0 = num_v); > num_v for a row partition of a larger graph
 };
 
 namespace spmm_b200 {

@@ -25,6 +25,9 @@ namespace spmm_b200 {
 
 void free_plan(Plan &p) {
     cudaFree(p.d_row_perm);
+    cudaFree(p.d_light_desc);
+    cudaFree(p.d_seg_hrow);
+    cudaFree(p.d_seg_count);
     cudaFree(p.d_heavy_rows);
     cudaFree(p.d_heavy_seg0);
     cudaFree(p.d_seg_desc);
@@ -35,25 +38,25 @@ void free_plan(Plan &p) {
 
 static inline int bit_length(unsigned x) { return x ? 32 - __builtin_clz(x) : 0; }
 
-int auto_seg_len(long long nnz) {
-    // long enough to amortise the segment prologue, short enough that the longest task is a
-    // small share of one SM's work: next power of two of nnz/16384, clamped to [256, 4096]
-    long long t = nnz / 16384;
-    int l = 256;
-    while (l < t && l < 4096) l <<= 1;
+int auto_seg_len(long long nnz, int lanes) {
+    (void)lanes;
+    // Rows longer than this are cut into segments (one warp each, all lane groups on the same
+    // row). Measured on B200 (profiles/r01_sweep.md): next power of two of nnz/65536, clamped
+    // to [128, 1024] — short enough that the longest whole row is a small share of an SM's work
+    // and long rows spread over many SMs, long enough to amortise the per-segment partial.
+    long long t = nnz / 65536;
+    int l = 128;
+    while (l < t && l < 1024) l <<= 1;
     return l;
 }
 
 int auto_kslice(int num_v, int feat) {
+    (void)num_v;
     if (feat % 4 != 0) return feat;
-    // widest slice whose share of B (num_v * kslice * 4 bytes) stays well inside the 126 MB L2
-    const long long budget = 48ll << 20;
-    int ks = 256;
-    while (ks > 32 && (long long)num_v * ks * 4 > budget) ks >>= 1;
-    if (ks > feat) {
-        ks = (feat + 3) & ~3;
-    }
-    return ks;
+    // Measured on B200 (profiles/r01_sweep.md): narrower feature slices never paid for the extra
+    // passes over col/val — the 126 MB L2 keeps the hot B rows even when B is larger than L2 —
+    // so a pass covers up to 256 columns (32 lanes x 2 float4).
+    return feat < 256 ? ((feat + 3) & ~3) : 256;
 }
 
 // Host-only core of the plan (also exported as spmm_b200_plan_host for CPU-side tests).
@@ -133,7 +136,8 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     if (K > 0 && p.kslice > ((K + 3) & ~3)) p.kslice = (K + 3) & ~3;
     p.n_slices = (K > 0) ? (K + p.kslice - 1) / p.kslice : 0;
     if (!p.scalar && K > 0) shape_for_kslice(p.kslice, &p.lanes, &p.vec);
-    p.seg_len = h->opt_seg_len > 0 ? (int)h->opt_seg_len : auto_seg_len(h->num_e);
+    p.seg_len = h->opt_seg_len > 0 ? (int)h->opt_seg_len : auto_seg_len(h->num_e, p.lanes);
+    p.tune = (int)h->opt_tune;
     if (p.scalar) p.seg_len = 0x7fffffff;   // scalar fallback keeps every row whole
 
     std::vector<int> ptr((size_t)M + 1, 0);
@@ -164,10 +168,25 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         SB_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, stream));
         return 0;
     };
-    if (h->opt_reorder || p.n_heavy > 0) {
-        if ((rc = upload((void **)&p.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
+    if ((rc = upload((void **)&p.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
+    {
+        std::vector<int4> light((size_t)p.n_light);
+        for (int i = 0; i < p.n_light; ++i) {
+            const int r = row_perm[i];
+            light[i] = make_int4(r, ptr[r], ptr[r + 1] - ptr[r], 0);
+        }
+        if ((rc = upload((void **)&p.d_light_desc, light.data(), sizeof(int4) * light.size()))) return rc;
+        SB_CUDA(cudaStreamSynchronize(stream));
     }
     if (p.n_heavy > 0) {
+        std::vector<int> seg_hrow((size_t)p.n_seg);
+        for (int hr = 0; hr < p.n_heavy; ++hr)
+            for (int sgm = heavy_seg0[hr]; sgm < heavy_seg0[hr + 1]; ++sgm) seg_hrow[sgm] = hr;
+        if ((rc = upload((void **)&p.d_seg_hrow, seg_hrow.data(), sizeof(int) * seg_hrow.size()))) return rc;
+        SB_CUDA(cudaStreamSynchronize(stream));
+        const size_t ncnt = (size_t)p.n_heavy * p.n_slices;
+        SB_CUDA(cudaMalloc((void **)&p.d_seg_count, sizeof(int) * ncnt));
+        SB_CUDA(cudaMemsetAsync(p.d_seg_count, 0, sizeof(int) * ncnt, stream));
         if ((rc = upload((void **)&p.d_heavy_rows, heavy_rows.data(), sizeof(int) * heavy_rows.size()))) return rc;
         if ((rc = upload((void **)&p.d_heavy_seg0, heavy_seg0.data(), sizeof(int) * heavy_seg0.size()))) return rc;
         if ((rc = upload((void **)&p.d_seg_desc, segs.data(), sizeof(SegDesc) * segs.size()))) return rc;
@@ -183,7 +202,7 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
 }  // namespace spmm_b200
 
 // Host-only plan for CPU-side callers and tests (declared in include/spmm_b200.h).
-extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, long long seg_len, int reorder, int *row_perm,
+extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, int feat_in, long long seg_len, int reorder, int *row_perm,
                                    int *n_light, int *heavy_rows, int *n_heavy, int *heavy_seg0, int *seg_desc,
                                    int *n_seg, long long *panel_len) {
     using namespace spmm_b200;
@@ -191,7 +210,11 @@ extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, long long seg_le
         set_error("spmm_b200_plan_host: bad arguments");
         return SPMM_B200_EINVAL;
     }
-    if (seg_len <= 0) seg_len = auto_seg_len(h_ptr[num_v]);
+    if (seg_len <= 0) {
+        int lanes = 32, vec = 1;
+        if (feat_in > 0 && feat_in % 4 == 0) shape_for_kslice(auto_kslice(num_v, feat_in), &lanes, &vec);
+        seg_len = (feat_in % 4 != 0) ? 0x7fffffffll : auto_seg_len(h_ptr[num_v], lanes);
+    }
     if (seg_len > 0x7fffffffll) seg_len = 0x7fffffffll;
     std::vector<int> rp, hr, hs;
     std::vector<SegDesc> segs;

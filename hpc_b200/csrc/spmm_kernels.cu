@@ -89,18 +89,54 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
         : "memory");
 }
 
-// ---- light rows ----------------------------------------------------------------------------
+// ---- the SpMM kernel ------------------------------------------------------------------------
+//
+// One launch. Warp tasks are laid out heavy segments first (longest work first), then light
+// rows in plan order; a warp picks its path from its global index, so the tail of the heavy
+// segments overlaps the start of the light rows and nothing waits on a second launch.
+//
+// TUNE selects a measured variant (option "tune"; profiles/r01_sweep.md):
+//   0: 8/VEC gathers in flight per lane group, <= 80 registers (3 CTAs of 256 threads per SM)
+//   1: as 0, B rows loaded with L1::no_allocate
+//   2: 4/VEC gathers in flight, <= 64 registers (4 CTAs/SM)
+//   3: as 0, L2 eviction hints: B rows evict_last, col/val/C evict_first
+template <int TUNE>
+struct Tune {
+    static constexpr int kMinBlocks = TUNE == 2 ? 4 : 3;
+    static constexpr int kUnrollBytes = TUNE == 2 ? 4 : 8;   // float4 per lane in flight
+};
 
-template <int LANES, int VEC>
-__global__ void __launch_bounds__(256) spmm_light_kernel(const RunArgs a) {
+template <int TUNE>
+__device__ __forceinline__ float4 ld_b(const float *p, uint64_t pol) {
+    if (TUNE == 1) {
+        float4 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+        return r;
+    } else if (TUNE == 3) {
+        float4 r;
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+        return r;
+    } else {
+        return ld_b_row(p);
+    }
+}
+template <int TUNE>
+__device__ __forceinline__ uint64_t b_policy() {
+    uint64_t pol = 0;
+    if (TUNE == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+template <int LANES, int VEC, int TUNE>
+__device__ __forceinline__ void light_rows(const RunArgs &a, long long gw, int lane) {
     constexpr int GROUPS = 32 / LANES;
-    constexpr int UMAX = (VEC == 1) ? 8 : 4;
-    constexpr int U = LANES < UMAX ? LANES : UMAX;   // gathers in flight per lane group
+    constexpr int UMAX = Tune<TUNE>::kUnrollBytes / VEC;
+    constexpr int U = LANES < UMAX ? LANES : UMAX;
     static_assert(LANES % U == 0, "unroll must tile the chunk");
-    const int lane = threadIdx.x & 31;
     const int l = lane % LANES;
     const int g = lane / LANES;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int slice = (int)(gw / a.light_tasks_per_slice);
     if (slice >= a.n_slices) return;
     const int task = (int)(gw - (long long)slice * a.light_tasks_per_slice);
@@ -108,9 +144,10 @@ __global__ void __launch_bounds__(256) spmm_light_kernel(const RunArgs a) {
 
     int row = -1, begin = 0, deg = 0;
     if (slot < a.n_light) {
-        row = a.row_perm ? a.row_perm[slot] : slot;
-        begin = a.ptr[row];
-        deg = a.ptr[row + 1] - begin;
+        const int4 d = __ldg(a.light_desc + slot);   // {row, begin, deg, 0}: one load instead of perm -> ptr
+        row = d.x;
+        begin = d.y;
+        deg = d.z;
     }
     int maxdeg = deg;
 #pragma unroll
@@ -120,12 +157,14 @@ __global__ void __launch_bounds__(256) spmm_light_kernel(const RunArgs a) {
     const int col0 = slice * a.kslice + l * 4;
     const int col_end = min(K, (slice + 1) * a.kslice);
     const float *bbase = a.vin + col0;
+    const uint64_t pol = b_policy<TUNE>();
     float4 acc[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     bool colok[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) colok[v] = col0 + v * LANES * 4 < col_end;
+    for (int v = 0; v < VEC; ++v) {
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        colok[v] = col0 + v * LANES * 4 < col_end;
+    }
 
     for (int base = 0; base < maxdeg; base += LANES) {
         const int i = base + l;
@@ -149,13 +188,13 @@ __global__ void __launch_bounds__(256) spmm_light_kernel(const RunArgs a) {
                 const float *brow = bbase + (size_t)ct * K;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
+                    if (ok[u] && colok[v]) b[u][v] = ld_b<TUNE>(brow + v * LANES * 4, pol);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) fma4(acc[v], b[u][v], wt[u]);
+                    if (ok[u] && colok[v]) fma4(acc[v], b[u][v], wt[u]);   // in CSR order: bit-exact chain
             }
         }
     }
@@ -167,55 +206,13 @@ __global__ void __launch_bounds__(256) spmm_light_kernel(const RunArgs a) {
     }
 }
 
-// K % 4 != 0: scalar lanes over the feature columns, one warp per row, same in-order chain.
-__global__ void __launch_bounds__(256) spmm_scalar_kernel(const RunArgs a) {
-    const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= a.n_light) return;
-    const int row = a.row_perm ? a.row_perm[gw] : (int)gw;
-    const int begin = a.ptr[row];
-    const int deg = a.ptr[row + 1] - begin;
-    const int K = a.feat;
-    for (int cb = 0; cb < K; cb += 32) {
-        const int col = cb + lane;
-        float acc = 0.f;
-        for (int base = 0; base < deg; base += 32) {
-            int c = 0;
-            float w = 0.f;
-            if (base + lane < deg) {
-                c = ld_stream_s32(a.idx + begin + base + lane);
-                w = ld_stream_f32(a.val + begin + base + lane);
-            }
-            const int n = min(32, deg - base);
-            for (int t = 0; t < n; ++t) {
-                const int ct = __shfl_sync(kFull, c, t);
-                const float wt = __shfl_sync(kFull, w, t);
-                if (col < K) acc = fmaf(__ldg(a.vin + (size_t)ct * K + col), wt, acc);
-            }
-        }
-        if (col < K) a.vout[(size_t)row * K + col] = acc;
-    }
-}
-
-// ---- heavy rows ----------------------------------------------------------------------------
-
-template <int LANES, int VEC>
-__global__ void __launch_bounds__(256) spmm_heavy_kernel(const RunArgs a) {
+template <int LANES, int VEC, int TUNE>
+__device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, int lane, int2 *buf, uint64_t *bars) {
     constexpr int GROUPS = 32 / LANES;
-    constexpr int U = (VEC == 1) ? 8 : 4;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
+    constexpr int U = Tune<TUNE>::kUnrollBytes / VEC;
     const int l = lane % LANES;
     const int g = lane / LANES;
-    const int nwarps = blockDim.x >> 5;
-    int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) +
-                     warp * kStages;
-
-    const long long gw = (long long)blockIdx.x * nwarps + warp;
     const int slice = (int)(gw / a.n_seg);
-    if (slice >= a.n_slices) return;
     const int seg = (int)(gw - (long long)slice * a.n_seg);
     const SegDesc d = a.seg_desc[seg];
     const int nchunks = (d.len + kChunk - 1) / kChunk;
@@ -243,6 +240,7 @@ __global__ void __launch_bounds__(256) spmm_heavy_kernel(const RunArgs a) {
     const int col0 = slice * a.kslice + l * 4;
     const int col_end = min(K, (slice + 1) * a.kslice);
     const float *bbase = a.vin + col0;
+    const uint64_t pol = b_policy<TUNE>();
     float4 acc[VEC];
     bool colok[VEC];
 #pragma unroll
@@ -270,7 +268,7 @@ __global__ void __launch_bounds__(256) spmm_heavy_kernel(const RunArgs a) {
                 const float *brow = bbase + (size_t)cv.x * K;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
+                    if (ok[u] && colok[v]) b[u][v] = ld_b<TUNE>(brow + v * LANES * 4, pol);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -298,29 +296,87 @@ __global__ void __launch_bounds__(256) spmm_heavy_kernel(const RunArgs a) {
         float *prow = a.part + (size_t)seg * K + col0;
 #pragma unroll
         for (int v = 0; v < VEC; ++v)
-            if (colok[v]) *reinterpret_cast<float4 *>(prow + v * LANES * 4) = acc[v];
+            if (colok[v]) __stcg(reinterpret_cast<float4 *>(prow + v * LANES * 4), acc[v]);
+        __threadfence();   // partial visible device-wide before this segment is counted
+    }
+    __syncwarp();
+
+    // Segment reduction without a second launch and without float atomics: the warp that
+    // finishes a row's last outstanding segment adds the partials IN SEGMENT ORDER, so the
+    // result does not depend on which warp that is. The counter returns to zero for the next run.
+    const int hrow = a.seg_hrow[seg];
+    const int s0 = a.heavy_seg0[hrow], s1 = a.heavy_seg0[hrow + 1];
+    int last = 0;
+    if (lane == 0) {
+        int *cnt = a.seg_count + (size_t)hrow * a.n_slices + slice;
+        last = atomicAdd(cnt, 1) == s1 - s0 - 1;
+        if (last) {
+            *cnt = 0;
+            __threadfence();
+        }
+    }
+    last = __shfl_sync(kFull, last, 0);
+    if (!last) return;
+    float *crow = a.vout + (size_t)d.row * K;
+    for (int col = slice * a.kslice + lane * 4; col < col_end; col += 128) {
+        const float *p = a.part + (size_t)s0 * K + col;
+        float4 sum = __ldcg(reinterpret_cast<const float4 *>(p));
+        for (int sgm = s0 + 1; sgm < s1; ++sgm) {
+            p += K;
+            const float4 x = __ldcg(reinterpret_cast<const float4 *>(p));
+            sum.x += x.x;
+            sum.y += x.y;
+            sum.z += x.z;
+            sum.w += x.w;
+        }
+        st_c_row(crow + col, sum);
     }
 }
 
-// one thread per (heavy row, float4 column): partials added in segment order
-__global__ void __launch_bounds__(256) spmm_fixup_kernel(const RunArgs a) {
-    const int k4 = a.feat >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)a.n_heavy * k4) return;
-    const int hrow = (int)(t / k4);
-    const int c4 = (int)(t - (long long)hrow * k4);
-    const int s0 = a.heavy_seg0[hrow], s1 = a.heavy_seg0[hrow + 1];
-    const float4 *p = reinterpret_cast<const float4 *>(a.part) + (size_t)s0 * k4 + c4;
-    float4 acc = *p;
-    for (int s = s0 + 1; s < s1; ++s) {
-        p += k4;
-        const float4 x = *p;
-        acc.x += x.x;
-        acc.y += x.y;
-        acc.z += x.z;
-        acc.w += x.w;
+template <int LANES, int VEC, int TUNE>
+__global__ void __launch_bounds__(256, Tune<TUNE>::kMinBlocks) spmm_kernel(const RunArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    if (gw < a.heavy_tasks) {
+        int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
+        uint64_t *bars =
+            reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages;
+        heavy_segment<LANES, VEC, TUNE>(a, gw, lane, buf, bars);
+    } else {
+        light_rows<LANES, VEC, TUNE>(a, gw - a.heavy_tasks, lane);
     }
-    st_c_row(a.vout + (size_t)a.heavy_rows[hrow] * a.feat + c4 * 4, acc);
+}
+
+// K % 4 != 0: scalar lanes over the feature columns, one warp per row, same in-order chain.
+__global__ void __launch_bounds__(256) spmm_scalar_kernel(const RunArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= a.n_light) return;
+    const int4 d = __ldg(a.light_desc + gw);
+    const int row = d.x, begin = d.y, deg = d.z;
+    const int K = a.feat;
+    for (int cb = 0; cb < K; cb += 32) {
+        const int col = cb + lane;
+        float acc = 0.f;
+        for (int base = 0; base < deg; base += 32) {
+            int c = 0;
+            float w = 0.f;
+            if (base + lane < deg) {
+                c = ld_stream_s32(a.idx + begin + base + lane);
+                w = ld_stream_f32(a.val + begin + base + lane);
+            }
+            const int n = min(32, deg - base);
+            for (int t = 0; t < n; ++t) {
+                const int ct = __shfl_sync(kFull, c, t);
+                const float wt = __shfl_sync(kFull, w, t);
+                if (col < K) acc = fmaf(__ldg(a.vin + (size_t)ct * K + col), wt, acc);
+            }
+        }
+        if (col < K) a.vout[(size_t)row * K + col] = acc;
+    }
 }
 
 // ---- preprocessing / support kernels ---------------------------------------------------------
@@ -376,26 +432,20 @@ __global__ void __launch_bounds__(256) valid_kernel(const float *y, const float 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
 }
 
-template <int LANES, int VEC>
-int launch_shape(const RunArgs &a, int block, cudaStream_t stream, int *launches) {
+template <int LANES, int VEC, int TUNE>
+void launch_tuned(const RunArgs &a, int block, cudaStream_t stream) {
     const int warps = block / 32;
-    if (a.n_seg > 0) {
-        const long long tasks = (long long)a.n_seg * a.n_slices;
-        const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
-        spmm_heavy_kernel<LANES, VEC><<<(unsigned)((tasks + warps - 1) / warps), block, smem, stream>>>(a);
-        ++*launches;
-    }
-    if (a.n_light > 0) {
-        const long long tasks = (long long)a.light_tasks_per_slice * a.n_slices;
-        spmm_light_kernel<LANES, VEC><<<(unsigned)((tasks + warps - 1) / warps), block, 0, stream>>>(a);
-        ++*launches;
-    }
-    if (a.n_heavy > 0) {
-        const long long threads = (long long)a.n_heavy * (a.feat >> 2);
-        spmm_fixup_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a);
-        ++*launches;
-    }
-    return 0;
+    const long long tasks = a.heavy_tasks + (long long)a.light_tasks_per_slice * a.n_slices;
+    const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
+    spmm_kernel<LANES, VEC, TUNE><<<(unsigned)((tasks + warps - 1) / warps), block, smem, stream>>>(a);
+}
+
+template <int LANES, int VEC>
+void launch_shape(const RunArgs &a, int block, int tune, cudaStream_t stream) {
+    if (tune == 1) launch_tuned<LANES, VEC, 1>(a, block, stream);
+    else if (tune == 2) launch_tuned<LANES, VEC, 2>(a, block, stream);
+    else if (tune == 3) launch_tuned<LANES, VEC, 3>(a, block, stream);
+    else launch_tuned<LANES, VEC, 0>(a, block, stream);
 }
 
 }  // namespace
@@ -404,47 +454,46 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
                 int *launches) {
     const Plan &p = h->plan;
     RunArgs a;
-    a.ptr = h->d_ptr;
     a.idx = h->d_idx;
     a.val = h->d_val;
     a.vin = vin;
     a.vout = vout;
-    a.num_v = h->num_v;
     a.feat = h->feat;
     a.kslice = p.kslice;
     a.n_slices = p.n_slices;
-    a.row_perm = p.d_row_perm;
+    a.light_desc = p.d_light_desc;
     a.n_light = p.n_light;
     a.seg_desc = p.d_seg_desc;
+    a.seg_hrow = p.d_seg_hrow;
+    a.seg_count = p.d_seg_count;
     a.panel = p.d_panel;
     a.part = p.d_part;
     a.n_seg = p.n_seg;
-    a.heavy_rows = p.d_heavy_rows;
     a.heavy_seg0 = p.d_heavy_seg0;
-    a.n_heavy = p.n_heavy;
+    a.heavy_tasks = (long long)p.n_seg * p.n_slices;
     *launches = 0;
     if (h->num_v == 0 || h->feat == 0) return 0;
     if (p.scalar) {
         a.light_tasks_per_slice = a.n_light;
         const int warps = p.block / 32;
         spmm_scalar_kernel<<<(unsigned)((a.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
-        ++*launches;
     } else {
         const int groups = 32 / p.lanes;
         a.light_tasks_per_slice = (a.n_light + groups - 1) / groups;
         switch (p.lanes * 10 + p.vec) {
-            case 11: launch_shape<1, 1>(a, p.block, stream, launches); break;
-            case 21: launch_shape<2, 1>(a, p.block, stream, launches); break;
-            case 41: launch_shape<4, 1>(a, p.block, stream, launches); break;
-            case 81: launch_shape<8, 1>(a, p.block, stream, launches); break;
-            case 161: launch_shape<16, 1>(a, p.block, stream, launches); break;
-            case 321: launch_shape<32, 1>(a, p.block, stream, launches); break;
-            case 322: launch_shape<32, 2>(a, p.block, stream, launches); break;
+            case 11: launch_shape<1, 1>(a, p.block, p.tune, stream); break;
+            case 21: launch_shape<2, 1>(a, p.block, p.tune, stream); break;
+            case 41: launch_shape<4, 1>(a, p.block, p.tune, stream); break;
+            case 81: launch_shape<8, 1>(a, p.block, p.tune, stream); break;
+            case 161: launch_shape<16, 1>(a, p.block, p.tune, stream); break;
+            case 321: launch_shape<32, 1>(a, p.block, p.tune, stream); break;
+            case 322: launch_shape<32, 2>(a, p.block, p.tune, stream); break;
             default:
                 set_error("unsupported kernel shape lanes=%d vec=%d", p.lanes, p.vec);
                 return SPMM_B200_EINVAL;
         }
     }
+    ++*launches;
     SB_CUDA(cudaGetLastError());
     return 0;
 }

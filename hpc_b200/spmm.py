@@ -67,12 +67,16 @@ class SpMM:
 class SpMMB200(SpMM):
     """The engine, in the slot of SpMMOpt (PA4/handout/src/spmm_opt.cu:3-11)."""
 
-    def __init__(self, g: CSR, feat_in: int, **options):
+    def __init__(self, g: CSR, feat_in: int, b_rows: int = 0, **options):
+        """b_rows: rows of B when g is a row block of a larger graph (columns index the full B)."""
         super().__init__(g, feat_in)
+        self.b_rows = int(b_rows) or g.num_v
         h = C.c_void_p()
         check(lib.spmm_b200_create(_ptr(g.ptr), _ptr(g.idx), _ptr(g.val), g.num_v, g.num_e,
                                    self.feat_in, C.byref(h)))
         self._h = h
+        if self.b_rows != g.num_v:
+            self.set_option("b_rows", self.b_rows)
         for k, v in options.items():
             self.set_option(k, v)
 
@@ -84,8 +88,7 @@ class SpMMB200(SpMM):
         check(lib.spmm_b200_set_feat(self._h, self.feat_in))
 
     def _check_io(self, vin, vout):
-        n = self.num_v * self.feat_in
-        for name, t in (("vin", vin), ("vout", vout)):
+        for name, t, n in (("vin", vin, self.b_rows * self.feat_in), ("vout", vout, self.num_v * self.feat_in)):
             if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
                 raise ValueError(f"{name}: need a contiguous CUDA float32 tensor of >= {n} elements")
 
@@ -97,10 +100,16 @@ class SpMMB200(SpMM):
         self._check_io(vin, vout)
         check(lib.spmm_b200_run(self._h, _ptr(vin), _ptr(vout), _stream()))
 
+    def run_profiled(self, vin, vout) -> float:
+        """run + the kernel's device time in ms (synchronises)."""
+        self._check_io(vin, vout)
+        ms = C.c_float(0)
+        check(lib.spmm_b200_run_profiled(self._h, _ptr(vin), _ptr(vout), _stream(), C.byref(ms)))
+        return ms.value
+
     def run_host(self, h_vin: torch.Tensor, h_vout: torch.Tensor) -> None:
         """H2D(vin) -> run -> D2H(vout) -> sync, host (ideally pinned) float32 tensors."""
-        n = self.num_v * self.feat_in
-        for name, t in (("h_vin", h_vin), ("h_vout", h_vout)):
+        for name, t, n in (("h_vin", h_vin, self.b_rows * self.feat_in), ("h_vout", h_vout, self.num_v * self.feat_in)):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
                 raise ValueError(f"{name}: need a contiguous host float32 tensor of >= {n} elements")
         check(lib.spmm_b200_run_host(self._h, C.c_void_p(h_vin.data_ptr()), C.c_void_p(h_vout.data_ptr()),
@@ -121,12 +130,14 @@ class SpMMB200(SpMM):
         out = {}
         for which, name, n in ((0, "row_perm", info["n_light"]), (1, "heavy_rows", info["n_heavy"]),
                                (2, "heavy_seg0", info["n_heavy"] + 1 if info["n_heavy"] else 0),
-                               (3, "seg_desc", info["n_seg"] * 4), (4, "panel", info["panel_len"] * 2)):
+                               (3, "seg_desc", info["n_seg"] * 4), (4, "panel", info["panel_len"] * 2),
+                               (5, "light_desc", info["n_light"] * 4), (6, "seg_hrow", info["n_seg"])):
             a = np.empty(n, dtype=np.int32)
             check(lib.spmm_b200_plan_copy(self._h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
             out[name] = a
         out["seg_desc"] = out["seg_desc"].reshape(-1, 4)
         out["panel"] = out["panel"].reshape(-1, 2)
+        out["light_desc"] = out["light_desc"].reshape(-1, 4)
         return out
 
     def close(self) -> None:
@@ -166,12 +177,12 @@ def valid(y: torch.Tensor, y2: torch.Tensor, num: int) -> int:
     return out.value
 
 
-def plan_host(ptr: np.ndarray, seg_len: int = 0, reorder: bool = True) -> dict:
+def plan_host(ptr: np.ndarray, feat: int, seg_len: int = 0, reorder: bool = True) -> dict:
     """The row part of the plan from a host ptr array (spmm_b200_plan_host); no GPU needed."""
     ptr = np.ascontiguousarray(ptr, dtype=np.int32)
     m = len(ptr) - 1
     nl, nh, ns, pl = C.c_int(0), C.c_int(0), C.c_int(0), C.c_longlong(0)
-    args = (C.c_void_p(ptr.ctypes.data), m, int(seg_len), int(bool(reorder)))
+    args = (C.c_void_p(ptr.ctypes.data), m, int(feat), int(seg_len), int(bool(reorder)))
     check(lib.spmm_b200_plan_host(*args, None, C.byref(nl), None, C.byref(nh), None, None, C.byref(ns), C.byref(pl)))
     row_perm = np.empty(nl.value, np.int32)
     heavy_rows = np.empty(nh.value, np.int32)

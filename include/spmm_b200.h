@@ -44,6 +44,9 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "kslice"    feature columns per pass over the graph (0 = auto; else multiple of 4)
  *   "block"     threads per CTA (multiple of 32)
  *   "reorder"   1 = degree-bucketed row order (default), 0 = natural order
+ *   "tune"      measured kernel variant, 0 (default) .. 3, see hpc_b200/csrc/spmm_kernels.cu
+ *   "b_rows"    rows of B when A is a row block of a larger graph (0 = num_v); only
+ *               spmm_b200_run_host needs it, to size its copy of B
  * The reference's counterpart are the compile-time constants kBatchSize / kTasksPerBlock
  * (PA4/workspace/src/spmm_opt.cu:6-7). */
 int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value);
@@ -59,6 +62,10 @@ int spmm_b200_preprocess(spmm_b200_t h, const float *vin, float *vout, void *str
  * Asynchronous on `stream` (a cudaStream_t; NULL = the default stream, as in the reference).
  * Fully overwrites vout[num_v*feat_in]; does not depend on its previous contents. */
 int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream);
+
+/* run, plus the device time of its kernel in milliseconds (CUDA events on `stream` around the
+ * launch). Synchronises. Counterpart of getCUDATime (PA4/handout/include/util.h:131-139). */
+int spmm_b200_run_profiled(spmm_b200_t h, const float *vin, float *vout, void *stream, float *ms);
 
 /* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). */
 int spmm_b200_destroy(spmm_b200_t h);
@@ -98,6 +105,8 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *   2 heavy_seg0 int32[n_heavy+1]   first segment of each heavy row (prefix)
  *   3 seg_desc   int32[n_seg*4]     {row, panel_off, len, nnz_begin} per segment
  *   4 panel      int32[panel_len*2] {col, float bits of val} pairs, segment-major
+ *   5 light_desc int32[n_light*4]   {row, ptr[row], deg(row), 0} per light row, same order as row_perm
+ *   6 seg_hrow   int32[n_seg]       index into heavy_rows of each segment's row
  * Returns SPMM_B200_EINVAL when `bytes` is not the exact size. */
 int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);
 
@@ -105,8 +114,8 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);
  * preprocess uses after copying ptr to the host). Call once with the array arguments NULL to
  * get the counts, then with row_perm int32[n_light], heavy_rows int32[n_heavy], heavy_seg0
  * int32[n_heavy+1 (0 if none)], seg_desc int32[n_seg*4]. seg_len <= 0 selects the automatic
- * value for nnz = h_ptr[num_v]. */
-int spmm_b200_plan_host(const int *h_ptr, int num_v, long long seg_len, int reorder, int *row_perm,
+ * value for nnz = h_ptr[num_v] and feat_in. */
+int spmm_b200_plan_host(const int *h_ptr, int num_v, int feat_in, long long seg_len, int reorder, int *row_perm,
                         int *n_light, int *heavy_rows, int *n_heavy, int *heavy_seg0, int *seg_desc,
                         int *n_seg, long long *panel_len);
 

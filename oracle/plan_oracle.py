@@ -17,10 +17,23 @@ from __future__ import annotations
 import numpy as np
 
 
-def auto_seg_len(nnz: int) -> int:
-    t = nnz // 16384
-    l = 256
-    while l < t and l < 4096:
+def lanes_for(feat: int) -> int:
+    """lanes cooperating on one row for the automatic slice width (32 when feat % 4 != 0)."""
+    if feat % 4:
+        return 32
+    q = (auto_kslice(0, feat) + 3) // 4
+    l = 1
+    while l < q and l < 32:
+        l <<= 1
+    return l
+
+
+def auto_seg_len(nnz: int, feat: int) -> int:
+    if feat % 4:
+        return 0x7FFFFFFF
+    t = nnz // 65536
+    l = 128
+    while l < t and l < 1024:
         l <<= 1
     return l
 
@@ -28,12 +41,7 @@ def auto_seg_len(nnz: int) -> int:
 def auto_kslice(num_v: int, feat: int) -> int:
     if feat % 4:
         return feat
-    ks = 256
-    while ks > 32 and num_v * ks * 4 > (48 << 20):
-        ks >>= 1
-    if ks > feat:
-        ks = (feat + 3) & ~3
-    return ks
+    return (feat + 3) & ~3 if feat < 256 else 256
 
 
 def bit_length(deg: np.ndarray) -> np.ndarray:
@@ -73,7 +81,12 @@ def plan(ptr, idx, val, seg_len: int, reorder: bool = True) -> dict:
             panel.append(pairs)
             off += len(pairs)
         heavy_seg0.append(len(seg_desc))
+    light_desc = np.stack([row_perm.astype(np.int64), ptr[row_perm], deg[row_perm], np.zeros(len(row_perm), np.int64)],
+                          axis=1).astype(np.int32).reshape(-1, 4)
+    seg_hrow = np.repeat(np.arange(len(heavy_rows)), np.diff(heavy_seg0)).astype(np.int32) if len(heavy_rows) else np.zeros(0, np.int32)
     return {
+        "light_desc": light_desc,
+        "seg_hrow": seg_hrow,
         "row_perm": row_perm,
         "heavy_rows": heavy_rows,
         "heavy_seg0": np.asarray(heavy_seg0 if len(heavy_rows) else [], np.int32),

@@ -1,0 +1,371 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI.
+
+Bar: bit-exact for integer work (plan, panels, partitions, generated inputs) and for every output
+row the engine keeps whole (same in-order FMA chain as PA4/handout/src/spmm_ref.cu:10-14);
+rows split into segments are re-associated and must satisfy
+    |C - C_ref| <= 1e-5 * sum_i |B[idx_i, j] * val_i|
+(the north-star's rel 1e-5, taken relative to the magnitude of the summed terms), and the whole
+output must pass the reference's own criterion (valid.cu:8 + test_spmm.cu:43).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import hpc_b200 as H  # noqa: E402
+from conftest import tiny_csr  # noqa: E402
+from oracle import cpu as O  # noqa: E402
+from oracle import plan_oracle as P  # noqa: E402
+import refshim  # noqa: E402
+
+TOL = 1e-5
+DEV = "cuda"
+
+
+def dev_inputs(ptr, idx, K, seed=123, val=None, b=None, b_rows=None):
+    M, nnz = len(ptr) - 1, len(idx)
+    b_rows = b_rows or M
+    d_ptr = torch.from_numpy(np.ascontiguousarray(ptr, np.int32)).to(DEV)
+    d_idx = torch.from_numpy(np.ascontiguousarray(idx, np.int32)).to(DEV)
+    if val is None:
+        d_val = H.fill_normal(torch.empty(nnz, device=DEV), seed, 1)
+    else:
+        d_val = torch.from_numpy(np.ascontiguousarray(val, np.float32)).to(DEV)
+    if b is None:
+        vin = H.fill_normal(torch.empty(b_rows * K, device=DEV), seed, 2)
+    else:
+        vin = torch.from_numpy(np.ascontiguousarray(b, np.float32).ravel()).to(DEV)
+    vout = torch.full((max(1, M * K),), float("nan"), device=DEV)
+    return H.CSR(M, nnz, d_ptr, d_idx, d_val), vin, vout
+
+
+def run_engine(ptr, idx, K, val=None, b=None, **opts):
+    g, vin, vout = dev_inputs(ptr, idx, K, val=val, b=b)
+    op = H.SpMMB200(g, K, **opts)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    torch.cuda.synchronize()
+    M = g.num_v
+    return op, g, vin, vout, vout[: M * K].cpu().numpy().reshape(M, K)
+
+
+def check_against_oracle(ptr, idx, K, op, g, vin, got):
+    M = g.num_v
+    val, b = g.val.cpu().numpy(), vin.cpu().numpy()
+    ref = O.spmm_f32(ptr, idx, val, b, K)
+    assert not np.isnan(got).any()
+    pa = op.plan_arrays()
+    light = pa["row_perm"]
+    assert np.array_equal(got[light].view(np.int32), ref[light].view(np.int32)), "whole rows must be bit-exact"
+    ab = O.spmm_abssum(ptr, idx, val, b, K)
+    assert np.all(np.abs(got.astype(np.float64) - ref) <= TOL * ab + 1e-30)
+    # the reference's pass criterion, candidate first (test_spmm.cu:43)
+    assert O.validate_float(got, ref) < M * K // 10000 + 1
+    return ref
+
+
+# ---- the oracle is pinned to the reference's own kernel -------------------------------------------
+
+@pytest.mark.skipif(not refshim.available(), reason="oracle/_ref/libspmm_ref.so not built (needs /root/reference at build time)")
+def test_reference_kernel_pins_oracle_and_golden(golden_dir):
+    """spmm_kernel_ref (unmodified, sm_100a, -O3 --use_fast_math) == CPU oracle == stored golden outputs, bitwise."""
+    meta = json.load(open(os.path.join(golden_dir, "golden.json")))
+    data = np.load(os.path.join(golden_dir, "golden.npz"))
+    for case in meta["cases"]:
+        n, K = case["name"], case["K"]
+        ptr, idx = data[f"{n}_ptr"], data[f"{n}_idx"]
+        g, vin, vout = dev_inputs(ptr, idx, K, seed=case["seed"])
+        refshim.ref_spmm(g.ptr, g.idx, g.val, vin, vout, g.num_v, g.num_e, K)
+        got = vout[: g.num_v * K].cpu().numpy().reshape(g.num_v, K)
+        assert np.array_equal(got.view(np.int32), data[f"{n}_out"].view(np.int32).reshape(got.shape)), n
+        ora = O.spmm_f32(ptr, idx, g.val.cpu().numpy(), vin.cpu().numpy(), K, ftz=True)
+        assert np.array_equal(got.view(np.int32), ora.view(np.int32)), n
+
+
+@pytest.mark.skipif(not refshim.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("shape,K", [("c0", 32), ("arxiv", 32), ("arxiv", 256)])
+def test_engine_vs_reference_kernel(shape, K):
+    """BASELINE configs 0-2: engine vs the reference's kernel on identical device inputs."""
+    ptr, idx = H.gen_named_graph(shape)
+    op, g, vin, vout, got = run_engine(ptr, idx, K)
+    M = g.num_v
+    ref_out = torch.zeros(M * K, device=DEV)
+    refshim.ref_spmm(g.ptr, g.idx, g.val, vin, ref_out, M, g.num_e, K)
+    ref = ref_out.cpu().numpy().reshape(M, K)
+    light = op.plan_arrays()["row_perm"]
+    assert np.array_equal(got[light].view(np.int32), ref[light].view(np.int32))
+    # reference's own validator, reference's own argument order (test_spmm.cu:43)
+    assert refshim.ref_valid(vout, ref_out, M * K) < M * K // 10000 + 1
+    assert H.valid(vout, ref_out, M * K) == O.validate_float(got, ref)
+    # and the oracle agrees with the reference kernel bit for bit at this size too
+    ora = check_against_oracle(ptr, idx, K, op, g, vin, got)
+    assert np.array_equal(ora.view(np.int32), ref.view(np.int32))
+    op.close()
+
+
+# ---- engine vs oracle -----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape,K,opts", [
+    ("c0", 32, {}), ("c0", 32, {"seg_len": 16}), ("c0", 32, {"reorder": 0}), ("c0", 256, {"seg_len": 64, "kslice": 64}),
+    ("c0", 256, {"kslice": 128}), ("c0", 64, {}), ("c0", 128, {"block": 128}), ("c0", 512, {}), ("c0", 260, {}),
+    ("c0", 100, {}), ("c0", 20, {}), ("c0", 8, {}), ("c0", 4, {}), ("c0", 30, {}), ("c0", 7, {}), ("c0", 1, {}),
+    ("arxiv", 32, {}), ("arxiv", 256, {}), ("arxiv", 256, {"kslice": 32, "seg_len": 128}),
+    ("arxiv", 32, {"tune": 1}), ("arxiv", 256, {"tune": 2}), ("c0", 64, {"tune": 2, "seg_len": 32}), ("arxiv", 256, {"tune": 3}),
+])
+def test_engine_matches_oracle(shape, K, opts):
+    ptr, idx = H.gen_named_graph(shape)
+    op, g, vin, vout, got = run_engine(ptr, idx, K, **opts)
+    check_against_oracle(ptr, idx, K, op, g, vin, got)
+    op.close()
+
+
+def test_golden_vectors_through_engine(golden_dir):
+    meta = json.load(open(os.path.join(golden_dir, "golden.json")))
+    data = np.load(os.path.join(golden_dir, "golden.npz"))
+    for case in meta["cases"]:
+        n, K = case["name"], case["K"]
+        ptr, idx = data[f"{n}_ptr"], data[f"{n}_idx"]
+        g, vin, vout = dev_inputs(ptr, idx, K, seed=case["seed"])
+        op = H.SpMMB200(g, K, seg_len=1 << 20)      # every row whole => bit-exact with the stored output
+        op.preprocess(vin, vout)
+        op.run(vin, vout)
+        got = vout[: g.num_v * K].cpu().numpy().reshape(g.num_v, K)
+        assert np.array_equal(got.view(np.int32), data[f"{n}_out"].view(np.int32).reshape(got.shape)), n
+        op.close()
+
+
+EDGE = {
+    "all_rows_empty": ([[], [], [], []], 4),
+    "one_by_one": ([[(0, 2.0)]], 1),
+    "empty_first_last": ([[], [(0, 1.0), (2, -1.0)], []], 3),
+    "duplicate_columns": ([[(1, 1e8), (1, 1.0), (1, -1e8)], [(0, 1.0), (0, 1.0)]], 2),
+    "unsorted_columns": ([[(2, 1.0), (0, 2.0), (1, 3.0)], [], [(1, 1.0)]], 3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE))
+@pytest.mark.parametrize("K", [4, 32, 33])
+def test_edge_cases(name, K):
+    rows, m = EDGE[name]
+    ptr, idx, val = tiny_csr(rows)
+    rng = np.random.default_rng(5)
+    b = rng.normal(0, 1, (m, K)).astype(np.float32)
+    op, g, vin, vout, got = run_engine(ptr, idx, K, val=val, b=b)
+    ref = O.spmm_literal(ptr, idx, val, b, K)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+    op.close()
+
+
+@pytest.mark.parametrize("length", [255, 256, 257, 511, 513, 10000])
+@pytest.mark.parametrize("K", [32, 256])
+def test_single_long_row(length, K):
+    """Row lengths around the segment size (the student's kBatchSize = 256, spmm_opt.cu:6)."""
+    m = 12000
+    rng = np.random.default_rng(length)
+    cols = np.sort(rng.choice(m, length, replace=False)).astype(np.int32)
+    ptr = np.zeros(m + 1, np.int32)
+    ptr[4:] = length          # row 3 holds everything
+    ptr[m] = length + 1       # plus one entry in the last row
+    idx = np.concatenate([cols, [7]]).astype(np.int32)
+    op, g, vin, vout, got = run_engine(ptr, idx, K, seg_len=256)
+    info = op.plan_info()
+    assert info["n_heavy"] == (1 if length > 256 else 0)
+    check_against_oracle(ptr, idx, K, op, g, vin, got)
+    op.close()
+
+
+def test_nnz_zero_and_empty_graph():
+    ptr = np.zeros(6, np.int32)
+    idx = np.zeros(0, np.int32)
+    op, g, vin, vout, got = run_engine(ptr, idx, 32)
+    assert not got.any() and not np.isnan(got).any()
+    op.close()
+    g = H.CSR(0, 0, torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV),
+              torch.zeros(0, device=DEV))
+    op = H.SpMMB200(g, 32)
+    z = torch.zeros(1, device=DEV)
+    op.preprocess(z, z)
+    op.run(z, z)
+    torch.cuda.synchronize()
+    op.close()
+
+
+def test_call_protocol_and_idempotence():
+    ptr, idx = H.gen_named_graph("c0")
+    K = 32
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    op = H.SpMMB200(g, K, seg_len=64)
+    with pytest.raises(H.SpmmB200Error) as e:
+        op.run(vin, vout)                 # run before preprocess
+    assert e.value.code == -2
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    first = vout.clone()
+    vout.fill_(float("inf"))              # run must not depend on vout's contents (unlike spmm_opt.cu:34,67-68)
+    for _ in range(3):
+        op.run(vin, vout)
+    assert torch.equal(first, vout)
+    # other buffers than the ones given to preprocess, on a non-default stream
+    vin2 = H.fill_normal(torch.empty_like(vin), 9, 9)
+    vout2 = torch.empty_like(vout)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        op.run(vin2, vout2)
+    s.synchronize()
+    ref = O.spmm_f32(ptr, idx, g.val.cpu().numpy(), vin2.cpu().numpy(), K)
+    ab = O.spmm_abssum(ptr, idx, g.val.cpu().numpy(), vin2.cpu().numpy(), K)
+    assert np.all(np.abs(vout2.cpu().numpy().reshape(-1, K).astype(np.float64) - ref) <= TOL * ab + 1e-30)
+    # set_feat invalidates the plan
+    op.set_feat(16)
+    with pytest.raises(H.SpmmB200Error) as e:
+        op.run(vin, vout)
+    assert e.value.code == -2
+    # misaligned vin is refused, not silently mis-read
+    op.set_feat(K)
+    op.preprocess(vin, vout)
+    big = torch.zeros(vin.numel() + 8, device=DEV)
+    with pytest.raises(H.SpmmB200Error) as e:
+        op.run(big[1:], vout)
+    assert e.value.code == -1
+    op.close()
+
+
+def test_run_host_matches_device_run():
+    ptr, idx = H.gen_named_graph("c0")
+    K = 64
+    op, g, vin, vout, got = run_engine(ptr, idx, K)
+    h_in = vin.cpu().pin_memory()
+    h_out = torch.empty(g.num_v * K).pin_memory()
+    op.run_host(h_in, h_out)
+    assert np.array_equal(h_out.numpy().view(np.int32), got.ravel().view(np.int32))
+    assert op.run_profiled(vin, vout) > 0 and op.launches_per_run == 1
+    op.close()
+
+
+# ---- integer paths: bit-exact -----------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape,seg_len,reorder", [("c0", 0, 1), ("c0", 16, 1), ("c0", 16, 0), ("arxiv", 0, 1), ("arxiv", 100, 1)])
+def test_plan_matches_oracle(shape, seg_len, reorder):
+    ptr, idx = H.gen_named_graph(shape)
+    g, vin, vout = dev_inputs(ptr, idx, 32)
+    op = H.SpMMB200(g, 32, seg_len=seg_len, reorder=reorder)
+    op.preprocess(vin, vout)
+    info = op.plan_info()
+    want = P.plan(ptr, idx, g.val.cpu().numpy(), info["seg_len"], bool(reorder))
+    got = op.plan_arrays()
+    assert info["seg_len"] == (seg_len or P.auto_seg_len(len(idx), 32))
+    assert info["kslice"] == P.auto_kslice(g.num_v, 32)
+    for k in ("row_perm", "light_desc", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
+        assert np.array_equal(got[k], want[k]), k
+    host = H.plan_host(ptr, 32, seg_len, bool(reorder))
+    for k in ("row_perm", "heavy_rows", "heavy_seg0", "seg_desc"):
+        assert np.array_equal(host[k], want[k]), k
+    op.close()
+
+
+def test_fill_and_valid_match_oracle():
+    for n, seed, stream in [(1, 123, 0), (1000, 123, 1), (1 << 20, 7, 5)]:
+        t = H.fill_normal(torch.empty(n, device=DEV), seed, stream)
+        assert np.array_equal(t.cpu().numpy(), O.fill_normal(n, seed, stream))
+    t = H.fill_normal(torch.empty(4096, device=DEV), 3, 4, mean=1.5, stddev=2.0)
+    assert np.array_equal(t.cpu().numpy(), O.fill_normal(4096, 3, 4, 1.5, 2.0))
+    a = H.allocate(1000)
+    assert a.numel() == 1024                      # data.h:27 rounds up to 512 elements
+    rng = np.random.default_rng(0)
+    y = rng.normal(0, 1, 100000).astype(np.float32)
+    y2 = (y * (1 + rng.normal(0, 0.01, y.size))).astype(np.float32)
+    y[:10] = 0
+    y2[:5] = 0
+    dy, dy2 = torch.from_numpy(y).to(DEV), torch.from_numpy(y2).to(DEV)
+    want = O.validate_float(y, y2)
+    assert H.valid(dy, dy2, y.size) == want
+    if refshim.available():
+        # the handout's divide is the fast-math approximate one: allow the 1e-2 boundary cases
+        assert abs(refshim.ref_valid(dy, dy2, y.size) - want) <= 3
+
+
+def test_row_partitions_reproduce_full_result():
+    """row blocks balanced by nnz, B replicated; concatenated block results equal the
+    single-GPU result bit for bit (per-row arithmetic depends only on the row and seg_len)."""
+    ptr, idx = H.gen_named_graph("arxiv")
+    K = 32
+    opf, g, vin, vout, full = run_engine(ptr, idx, K, seg_len=256)
+    M = g.num_v
+    val = g.val
+    for parts in (2, 8):
+        bounds = H.partition_rows(ptr, parts)
+        assert np.array_equal(bounds, P.partition_rows(ptr, parts))
+        outs = []
+        for r in range(parts):
+            r0, r1 = int(bounds[r]), int(bounds[r + 1])
+            lptr = H.rebase_ptr(ptr, r0, r1)
+            e0, e1 = int(ptr[r0]), int(ptr[r1])
+            gl = H.CSR(r1 - r0, e1 - e0, torch.from_numpy(lptr).to(DEV), g.idx[e0:e1].clone(), val[e0:e1].clone())
+            o = torch.full((max(1, (r1 - r0) * K),), float("nan"), device=DEV)
+            op = H.SpMMB200(gl, K, b_rows=M, seg_len=256)
+            op.preprocess(vin, o)
+            op.run(vin, o)
+            outs.append(o[: (r1 - r0) * K].cpu().numpy())
+            op.close()
+        cat = np.concatenate(outs).reshape(M, K)
+        assert np.array_equal(cat.view(np.int32), full.view(np.int32))
+    opf.close()
+
+
+# ---- BASELINE full sizes: size-independent properties ---------------------------------------------------
+
+def _full_size_properties(shape, K):
+    ptr, idx = H.gen_named_graph(shape)
+    op, g, vin, vout, _ = run_engine(ptr, idx, K)
+    M, nnz = g.num_v, g.num_e
+    C1 = vout[: M * K].view(M, K)
+    # (a) sampled row ranges against the oracle (bit-exact when whole, tolerance when split)
+    val_h, b_h = g.val.cpu().numpy(), vin.cpu().numpy()
+    deg = np.diff(ptr)
+    pa = op.plan_arrays()
+    heavy = set(pa["heavy_rows"].tolist())
+    picks = [0, M // 3, M - 64, int(np.argmax(deg)) - 3]
+    for r0 in picks:
+        r0 = max(0, min(M - 64, r0))
+        ref = O.spmm_f32(ptr, idx, val_h, b_h, K, row_begin=r0, row_end=r0 + 64)[r0:r0 + 64]
+        got = C1[r0:r0 + 64].cpu().numpy()
+        for i in range(64):
+            if (r0 + i) in heavy:
+                scale = np.abs(b_h.reshape(M, K)[idx[ptr[r0 + i]:ptr[r0 + i + 1]]] * val_h[ptr[r0 + i]:ptr[r0 + i + 1], None]).sum(0)
+                assert np.all(np.abs(got[i].astype(np.float64) - ref[i]) <= TOL * scale + 1e-30)
+            else:
+                assert np.array_equal(got[i].view(np.int32), ref[i].view(np.int32)), r0 + i
+    # (b) checksum of checksums: sum_r C[r,:] == sum_c (sum of column c's values) * B[c,:]   (fp64)
+    colw = torch.zeros(M, dtype=torch.float64, device=DEV)
+    colw.index_add_(0, g.idx.long(), g.val.double())
+    want = (colw[:, None] * vin.view(M, K).double()).sum(0)
+    got = C1.double().sum(0)
+    scale = (colw.abs()[:, None] * vin.view(M, K).double().abs()).sum(0)
+    assert torch.all((got - want).abs() <= 1e-6 * scale)
+    # (c) linearity in B: A(2*B) == 2*A(B) exactly (scaling by 2 commutes with rounding)
+    vin2 = vin * 2
+    vout2 = torch.empty_like(vout)
+    op.run(vin2, vout2)
+    assert torch.equal(vout2[: M * K], vout[: M * K] * 2)
+    # (d) idempotence
+    op.run(vin, vout2)
+    assert torch.equal(vout2[: M * K], vout[: M * K])
+    # (e) the reference's criterion against itself is clean (no NaN/Inf produced)
+    assert torch.isfinite(C1).all()
+    op.close()
+
+
+def test_reddit_k256_full_size_properties():
+    _full_size_properties("reddit", 256)
+
+
+def test_products_k256_full_size_properties():
+    _full_size_properties("products", 256)

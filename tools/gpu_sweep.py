@@ -94,20 +94,13 @@ def bench(name, K, optlist, iters=10):
 
 
 print(torch.cuda.get_device_name(0), flush=True)
-parity("c0", 32)
-parity("c0", 32, seg_len=16)
-parity("c0", 256, seg_len=64, kslice=64)
-parity("c0", 100)
-parity("c0", 30)
-parity("arxiv", 32)
-parity("arxiv", 256)
-parity("arxiv", 256, kslice=32, seg_len=128)
-
-bench("arxiv", 32, [{}, {"seg_len": 128}, {"seg_len": 512}, {"seg_len": 2048}, {"reorder": 0}, {"block": 128}])
-bench("arxiv", 256, [{}, {"kslice": 128}, {"kslice": 64}, {"kslice": 32}, {"seg_len": 512}])
-sw = [{"kslice": k} for k in (256, 128, 64, 32)] + [{"kslice": 64, "seg_len": s} for s in (1024, 100000)] + \
-     [{"kslice": 64, "reorder": 0}, {"kslice": 64, "block": 128}]
-bench("reddit", 256, sw, iters=5)
+if mode in ("quick", "full"):
+    parity("arxiv", 256, tune=1)
+    parity("arxiv", 32, tune=2)
+    parity("arxiv", 256, tune=3)
+    bench("arxiv", 32, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}, {"seg_len": 64}, {"seg_len": 256}])
+    bench("arxiv", 256, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}])
+    bench("reddit", 256, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}, {"seg_len": 512}, {"seg_len": 256}, {"seg_len": 128}], iters=5)
 if mode == "full":
-    bench("reddit", 32, [{}, {"seg_len": 1024}], iters=5)
-    bench("products", 256, [{"kslice": k} for k in (256, 128, 64, 32)], iters=5)
+    bench("reddit", 32, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}], iters=5)
+    bench("products", 256, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}, {"seg_len": 256}], iters=5)
