@@ -55,7 +55,7 @@ struct RunArgs {
 
 struct Plan {
     bool ready = false;
-    int seg_len = 0, kslice = 0, n_slices = 0, block = 256, lanes = 0, vec = 0, tune = 0;
+    int seg_len = 0, kslice = 0, n_slices = 0, block = 128, lanes = 0, vec = 0, tune = 0;
     bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
     int n_light = 0, n_heavy = 0, n_seg = 0;
     long long panel_len = 0;
@@ -78,7 +78,7 @@ struct spmm_b200_handle {
     const int *d_idx = nullptr;
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
-    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 256, opt_reorder = 1, opt_tune = 0;
+    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = 1, opt_tune = 0;
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_elems = 0, stage_in_elems = 0;

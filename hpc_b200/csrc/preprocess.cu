@@ -39,11 +39,15 @@ void free_plan(Plan &p) {
 static inline int bit_length(unsigned x) { return x ? 32 - __builtin_clz(x) : 0; }
 
 int auto_seg_len(long long nnz, int lanes) {
-    (void)lanes;
-    // Rows longer than this are cut into segments (one warp each, all lane groups on the same
-    // row). Measured on B200 (profiles/r01_sweep.md): next power of two of nnz/65536, clamped
-    // to [128, 1024] — short enough that the longest whole row is a small share of an SM's work
-    // and long rows spread over many SMs, long enough to amortise the per-segment partial.
+    // Rows longer than this are cut into nnz-balanced segments, one warp each, their col/val
+    // staged through shared memory by TMA. Measured on B200 (profiles/r01_sweep.md):
+    //  * a full warp per row (K >= 128): equal-sized staged work units beat whole-row warps from
+    //    ~256 nonzeros up on every graph shape;
+    //  * narrower lane groups (K < 128): a segment carries only lanes*16 bytes per nonzero, so the
+    //    per-segment partial + counter cost wants longer segments on big graphs (reddit K=32:
+    //    1024), while small graphs are tail-bound and want short ones (arxiv K=32: 128):
+    //    next power of two of nnz/65536, clamped to [128, 1024].
+    if (lanes >= 32) return 256;
     long long t = nnz / 65536;
     int l = 128;
     while (l < t && l < 1024) l <<= 1;

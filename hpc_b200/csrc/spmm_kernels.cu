@@ -96,24 +96,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // segments overlaps the start of the light rows and nothing waits on a second launch.
 //
 // TUNE selects a measured variant (option "tune"; profiles/r01_sweep.md):
-//   0: 8/VEC gathers in flight per lane group, <= 80 registers (3 CTAs of 256 threads per SM)
-//   1: as 0, B rows loaded with L1::no_allocate
-//   2: 4/VEC gathers in flight, <= 64 registers (4 CTAs/SM)
-//   3: as 0, L2 eviction hints: B rows evict_last, col/val/C evict_first
+//   0: 4/VEC gathers in flight per lane group, <= 64 registers (4 CTAs of 256 threads per SM)
+//   1: 8/VEC gathers in flight, <= 80 registers (3 CTAs/SM)
+//   2: 2/VEC gathers in flight, <= 48 registers (5 CTAs/SM)
+//   3: as 0, L2 eviction hint evict_last on B rows
 template <int TUNE>
 struct Tune {
-    static constexpr int kMinBlocks = TUNE == 2 ? 4 : 3;
-    static constexpr int kUnrollBytes = TUNE == 2 ? 4 : 8;   // float4 per lane in flight
+    static constexpr int kMinBlocks = TUNE == 1 ? 3 : (TUNE == 2 ? 5 : 4);
+    static constexpr int kUnrollBytes = TUNE == 1 ? 8 : (TUNE == 2 ? 2 : 4);   // float4 per lane in flight
 };
 
 template <int TUNE>
 __device__ __forceinline__ float4 ld_b(const float *p, uint64_t pol) {
-    if (TUNE == 1) {
-        float4 r;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-        return r;
-    } else if (TUNE == 3) {
+    if (TUNE == 3) {
         float4 r;
         asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
@@ -166,13 +161,21 @@ __device__ __forceinline__ void light_rows(const RunArgs &a, long long gw, int l
         colok[v] = col0 + v * LANES * 4 < col_end;
     }
 
+    // col/val of the next LANES nonzeros are requested before the current ones are consumed, so a
+    // row never waits for an index load and then again for the gathers that depend on it
+    int c = 0;
+    float w = 0.f;
+    if (l < deg) {
+        c = ld_stream_s32(a.idx + begin + l);
+        w = ld_stream_f32(a.val + begin + l);
+    }
     for (int base = 0; base < maxdeg; base += LANES) {
-        const int i = base + l;
-        int c = 0;
-        float w = 0.f;
-        if (i < deg) {
-            c = ld_stream_s32(a.idx + begin + i);
-            w = ld_stream_f32(a.val + begin + i);
+        int cn = 0;
+        float wn = 0.f;
+        const int in = base + LANES + l;
+        if (in < deg) {
+            cn = ld_stream_s32(a.idx + begin + in);
+            wn = ld_stream_f32(a.val + begin + in);
         }
         const int n = min(LANES, maxdeg - base);   // warp-uniform
         for (int t0 = 0; t0 < n; t0 += U) {
@@ -197,6 +200,8 @@ __device__ __forceinline__ void light_rows(const RunArgs &a, long long gw, int l
                     if (ok[u] && colok[v]) fma4(acc[v], b[u][v], wt[u]);   // in CSR order: bit-exact chain
             }
         }
+        c = cn;
+        w = wn;
     }
     if (row >= 0) {
         float *crow = a.vout + (size_t)row * K + col0;

@@ -31,6 +31,8 @@ def lanes_for(feat: int) -> int:
 def auto_seg_len(nnz: int, feat: int) -> int:
     if feat % 4:
         return 0x7FFFFFFF
+    if lanes_for(feat) >= 32:
+        return 256
     t = nnz // 65536
     l = 128
     while l < t and l < 1024:

@@ -369,3 +369,24 @@ def test_reddit_k256_full_size_properties():
 
 def test_products_k256_full_size_properties():
     _full_size_properties("products", 256)
+
+
+# ---- the reference's test driver, restated without gtest (tests/cpp/unit_tests.cpp) ---------------------
+
+def test_cpp_harness_validation_and_timing(tmp_path):
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "cpp", "unit_tests")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp")], check=True, capture_output=True)
+    # synthetic shape
+    r = subprocess.run([exe, "--shape", "arxiv", "--len", "32"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[  PASSED  ] 2 tests." in r.stdout
+    assert "time = " in r.stderr and "(double)" in r.stderr          # the line PA4/workspace/plot.py:13-27 parses
+    # reference file format: --dataset/--datadir, as run_all.sh:11 calls it
+    ptr, idx = H.gen_named_graph("c0")
+    H.write_graph(str(tmp_path), "c0", ptr, idx, text=True)
+    r = subprocess.run([exe, "--dataset", "c0", "--datadir", str(tmp_path), "--len", "256"], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "[  PASSED  ] 2 tests." in r.stdout, r.stdout + r.stderr

@@ -128,11 +128,14 @@ def test_plan_host_matches_oracle():
         for k in ("row_perm", "heavy_rows", "heavy_seg0", "seg_desc"):
             assert np.array_equal(got[k], want[k]), (name, k)
         assert got["panel_len"] == len(want["panel"])
-    # automatic cut-off: pow2ceil(nnz/65536) clamped to [128, 1024]
+    # automatic cut-off: 256 when a full warp covers the feature slice (K >= 128), else 128..1024 by nnz
+    assert P.auto_seg_len(114615892, 32) == 1024 and P.auto_seg_len(114615892, 64) == 1024 and P.auto_seg_len(20 << 20, 32) == 512
     ptr, idx = H.gen_named_graph("arxiv")
-    assert P.auto_seg_len(len(idx), 256) == 128 and P.auto_seg_len(len(idx), 32) == 128
-    assert P.auto_seg_len(114615892, 256) == 1024 and P.auto_seg_len(65536, 32) == 128 and P.auto_seg_len(40 << 20, 8) == 1024
+    assert P.auto_seg_len(len(idx), 256) == 256 and P.auto_seg_len(len(idx), 32) == 128 and P.auto_seg_len(1, 128) == 256
+    assert P.auto_seg_len(len(idx), 100) == 256 and P.auto_seg_len(len(idx), 64) == 128
     a, b = H.plan_host(ptr, 32), P.plan(ptr, idx, np.zeros(len(idx), np.float32), 128, True)
+    assert np.array_equal(a["seg_desc"], b["seg_desc"]) and np.array_equal(a["row_perm"], b["row_perm"])
+    a, b = H.plan_host(ptr, 256), P.plan(ptr, idx, np.zeros(len(idx), np.float32), 256, True)
     assert np.array_equal(a["seg_desc"], b["seg_desc"]) and np.array_equal(a["row_perm"], b["row_perm"])
     assert len(H.plan_host(ptr, 30)["heavy_rows"]) == 0       # scalar path keeps every row whole
     # cross-check with the student's task split (spmm_opt.cu:43-54): same number of pieces per row at 256

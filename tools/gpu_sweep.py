@@ -95,12 +95,9 @@ def bench(name, K, optlist, iters=10):
 
 print(torch.cuda.get_device_name(0), flush=True)
 if mode in ("quick", "full"):
-    parity("arxiv", 256, tune=1)
-    parity("arxiv", 32, tune=2)
-    parity("arxiv", 256, tune=3)
-    bench("arxiv", 32, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}, {"seg_len": 64}, {"seg_len": 256}])
-    bench("arxiv", 256, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}])
-    bench("reddit", 256, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}, {"seg_len": 512}, {"seg_len": 256}, {"seg_len": 128}], iters=5)
-if mode == "full":
-    bench("reddit", 32, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}], iters=5)
-    bench("products", 256, [{}, {"tune": 1}, {"tune": 2}, {"tune": 3}, {"seg_len": 256}], iters=5)
+    bench("reddit", 256, [{}, {"kslice": 128}, {"kslice": 64}, {"kslice": 64, "seg_len": 128}, {"kslice": 32, "seg_len": 128},
+                          {"reorder": 0}, {"reorder": 0, "block": 32}, {"reorder": 0, "block": 64}, {"block": 64}, {"block": 128}], iters=5)
+    bench("products", 256, [{}, {"reorder": 0}, {"reorder": 0, "block": 32}, {"reorder": 0, "block": 64}, {"block": 64}, {"block": 128},
+                            {"kslice": 128}, {"kslice": 128, "reorder": 0, "block": 32}], iters=5)
+    bench("arxiv", 32, [{}, {"block": 64}, {"block": 128}, {"reorder": 0, "block": 32}])
+    bench("arxiv", 256, [{}, {"block": 64}, {"block": 128}, {"reorder": 0, "block": 32}])
