@@ -21,6 +21,7 @@ class PlanInfo(C.Structure):
         ("seg_len", C.c_int), ("kslice", C.c_int), ("n_slices", C.c_int), ("block", C.c_int),
         ("n_light", C.c_int), ("n_heavy", C.c_int), ("n_seg", C.c_int),
         ("panel_len", C.c_longlong), ("lanes", C.c_int), ("vec", C.c_int),
+        ("n_col_blocks", C.c_int), ("col_begin", C.c_int), ("col_end", C.c_int),
     ]
 
     def as_dict(self):
@@ -43,6 +44,7 @@ SIGNATURES = {
     "spmm_b200_run_host": (_I, [_P, _P, _P, _P]),
     "spmm_b200_last_error": (C.c_char_p, []),
     "spmm_b200_launches_per_run": (_I, [_P]),
+    "spmm_b200_plan_select": (_I, [_P, _I]),
     "spmm_b200_plan_info": (_I, [_P, C.POINTER(PlanInfo)]),
     "spmm_b200_plan_copy": (_I, [_P, _I, _P, C.c_size_t]),
     "spmm_b200_plan_host": (_I, [_P, _I, _I, _LL, _I, _P, C.POINTER(_I), _P, C.POINTER(_I), _P, _P, C.POINTER(_I),

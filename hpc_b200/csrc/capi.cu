@@ -74,6 +74,7 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     else if (!strcmp(name, "block") && value >= 32 && value <= 256 && value % 32 == 0) h->opt_block = value;
     else if (!strcmp(name, "reorder") && (value == 0 || value == 1)) h->opt_reorder = value;
     else if (!strcmp(name, "tune") && value >= 0 && value <= 3) h->opt_tune = value;
+    else if (!strcmp(name, "col_blocks") && value >= 0 && value <= 64) h->opt_col_blocks = value;
     else if (!strcmp(name, "b_rows") && value >= 0 && value <= 0x7fffffffll) {
         h->b_rows = (int)value;   // does not touch the plan
         return 0;
@@ -181,12 +182,22 @@ int spmm_b200_destroy(spmm_b200_t h) {
 
 int spmm_b200_launches_per_run(spmm_b200_t h) { return h ? h->plan.launches : 0; }
 
+int spmm_b200_plan_select(spmm_b200_t h, int col_block) {
+    if (!h || !h->plan.ready || col_block < 0 || col_block >= h->plan.n_col_blocks) {
+        set_error("spmm_b200_plan_select: no such column block");
+        return SPMM_B200_EINVAL;
+    }
+    h->plan_select = col_block;
+    return 0;
+}
+
 int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info) {
     if (!h || !info || !h->plan.ready) {
         set_error("spmm_b200_plan_info: no plan");
         return h && info ? SPMM_B200_ESTATE : SPMM_B200_EINVAL;
     }
     const Plan &p = h->plan;
+    const BlockPlan &b = p.blocks[h->plan_select];
     info->num_v = h->num_v;
     info->num_e = h->num_e;
     info->feat_in = h->feat;
@@ -194,12 +205,15 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info) {
     info->kslice = p.kslice;
     info->n_slices = p.n_slices;
     info->block = p.block;
-    info->n_light = p.n_light;
-    info->n_heavy = p.n_heavy;
-    info->n_seg = p.n_seg;
-    info->panel_len = p.panel_len;
+    info->n_light = b.n_light;
+    info->n_heavy = b.n_heavy;
+    info->n_seg = b.n_seg;
+    info->panel_len = b.panel_len;
     info->lanes = p.lanes;
     info->vec = p.vec;
+    info->n_col_blocks = p.n_col_blocks;
+    info->col_begin = b.col_begin;
+    info->col_end = b.col_end;
     return 0;
 }
 
@@ -208,7 +222,8 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
         set_error("spmm_b200_plan_copy: no plan");
         return SPMM_B200_ESTATE;
     }
-    const Plan &p = h->plan;
+    const Plan &pl = h->plan;
+    const BlockPlan &p = pl.blocks[h->plan_select];
     const void *src = nullptr;
     size_t want = 0;
     switch (which) {
@@ -219,6 +234,10 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
         case 4: src = p.d_panel; want = sizeof(int2) * (size_t)p.panel_len; break;
         case 5: src = p.d_light_desc; want = sizeof(int4) * (size_t)p.n_light; break;
         case 6: src = p.d_seg_hrow; want = sizeof(int) * (size_t)p.n_seg; break;
+        case 7:
+            src = pl.d_split;
+            want = pl.n_col_blocks > 1 ? sizeof(int) * (size_t)(pl.n_col_blocks + 1) * h->num_v : 0;
+            break;
         default: set_error("spmm_b200_plan_copy: unknown array %d", which); return SPMM_B200_EINVAL;
     }
     if (bytes != want) {

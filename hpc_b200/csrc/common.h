@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "spmm_b200.h"
 
 namespace spmm_b200 {
@@ -51,12 +53,12 @@ struct RunArgs {
     float *part;               // [n_seg][K] partial sums
     int n_seg;
     long long heavy_tasks;     // n_seg * n_slices
+    int accumulate;            // 1: continue the chains from vout (column blocks after the first)
 };
 
-struct Plan {
-    bool ready = false;
-    int seg_len = 0, kslice = 0, n_slices = 0, block = 128, lanes = 0, vec = 0, tune = 0;
-    bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
+// The plan of one column block (the whole matrix when there is a single block).
+struct BlockPlan {
+    int col_begin = 0, col_end = 0;   // B rows [col_begin, col_end) are gathered in this pass
     int n_light = 0, n_heavy = 0, n_seg = 0;
     long long panel_len = 0;
     int *d_row_perm = nullptr;
@@ -68,6 +70,15 @@ struct Plan {
     int *d_seg_count = nullptr;
     int2 *d_panel = nullptr;
     float *d_part = nullptr;
+};
+
+struct Plan {
+    bool ready = false;
+    int seg_len = 0, kslice = 0, n_slices = 0, block = 128, lanes = 0, vec = 0, tune = 0;
+    bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
+    int n_col_blocks = 1;
+    int *d_split = nullptr;   // [(n_col_blocks+1)][num_v] start of each column block inside each row
+    std::vector<BlockPlan> blocks;
     int launches = 0;
 };
 
@@ -78,7 +89,8 @@ struct spmm_b200_handle {
     const int *d_idx = nullptr;
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
-    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = 1, opt_tune = 0;
+    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = 1, opt_tune = 0, opt_col_blocks = 0;
+    int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_elems = 0, stage_in_elems = 0;
@@ -94,6 +106,8 @@ void free_plan(Plan &p);
 // spmm_kernels.cu
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
                 int *launches);
+int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
+                      int *d_split, int *d_unsorted, cudaStream_t stream);
 int launch_build_panel(const SegDesc *d_seg, int n_seg, const int *d_idx, const float *d_val,
                        int2 *d_panel, cudaStream_t stream);
 int launch_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream_id, float mean,

@@ -24,15 +24,18 @@
 namespace spmm_b200 {
 
 void free_plan(Plan &p) {
-    cudaFree(p.d_row_perm);
-    cudaFree(p.d_light_desc);
-    cudaFree(p.d_seg_hrow);
-    cudaFree(p.d_seg_count);
-    cudaFree(p.d_heavy_rows);
-    cudaFree(p.d_heavy_seg0);
-    cudaFree(p.d_seg_desc);
-    cudaFree(p.d_panel);
-    cudaFree(p.d_part);
+    for (BlockPlan &b : p.blocks) {
+        cudaFree(b.d_row_perm);
+        cudaFree(b.d_light_desc);
+        cudaFree(b.d_heavy_rows);
+        cudaFree(b.d_heavy_seg0);
+        cudaFree(b.d_seg_desc);
+        cudaFree(b.d_seg_hrow);
+        cudaFree(b.d_seg_count);
+        cudaFree(b.d_panel);
+        cudaFree(b.d_part);
+    }
+    cudaFree(p.d_split);
     p = Plan();
 }
 
@@ -63,16 +66,31 @@ int auto_kslice(int num_v, int feat) {
     return feat < 256 ? ((feat + 3) & ~3) : 256;
 }
 
+// Column blocks: when B does not fit the L2, A is processed as n column blocks (C = sum_b A[:, b]·B[b, :]),
+// one pass each, so that every pass gathers from an L2-resident band of B and HBM sees B about once.
+// Worth it only while a row still has enough nonzeros per block to amortise re-reading its C row.
+int auto_col_blocks(long long b_rows, int feat, long long nnz, int num_v) {
+    const long long b_bytes = b_rows * feat * 4ll;
+    if (feat % 4 != 0 || num_v <= 0 || b_bytes <= (96ll << 20)) return 1;
+    const long long band = 48ll << 20;
+    long long nb = (b_bytes + band - 1) / band;
+    if (nb > 16) return 1;
+    if (nnz / num_v / nb < 64) return 1;
+    return (int)nb;
+}
+
 // Host-only core of the plan (also exported as spmm_b200_plan_host for CPU-side tests).
-int plan_rows_host(const int *ptr, int M, int seg_len, int reorder, std::vector<int> &row_perm,
-                   std::vector<int> &heavy_rows, std::vector<int> &heavy_seg0, std::vector<SegDesc> &segs,
-                   long long *panel_len_out) {
+// Row r owns CSR positions [rb[r], re[r]) (rb = ptr, re = ptr + 1 for the whole matrix; a column block
+// passes its own bounds). skip_empty drops rows with no nonzero in the block (passes after the first).
+int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder, int skip_empty,
+                   std::vector<int> &row_perm, std::vector<int> &heavy_rows, std::vector<int> &heavy_seg0,
+                   std::vector<SegDesc> &segs, long long *panel_len_out) {
     // stable counting sort by bucket, descending
     std::vector<int> order((size_t)M);
     if (reorder) {
         size_t cnt[34] = {0};
         for (int r = 0; r < M; ++r) {
-            const int d = ptr[r + 1] - ptr[r];
+            const int d = re[r] - rb[r];
             if (d < 0) {
                 set_error("CSR ptr decreases at row %d", r);
                 return SPMM_B200_EINVAL;
@@ -85,7 +103,7 @@ int plan_rows_host(const int *ptr, int M, int seg_len, int reorder, std::vector<
             start[b] = run;
             run += cnt[b];
         }
-        for (int r = 0; r < M; ++r) order[start[bit_length((unsigned)(ptr[r + 1] - ptr[r]))]++] = r;
+        for (int r = 0; r < M; ++r) order[start[bit_length((unsigned)(re[r] - rb[r]))]++] = r;
     } else {
         for (int r = 0; r < M; ++r) order[r] = r;
     }
@@ -98,8 +116,9 @@ int plan_rows_host(const int *ptr, int M, int seg_len, int reorder, std::vector<
     long long panel_len = 0;
     for (int k = 0; k < M; ++k) {
         const int r = order[k];
-        const int begin = ptr[r];
-        const int d = ptr[r + 1] - begin;
+        const int begin = rb[r];
+        const int d = re[r] - begin;
+        if (d == 0 && skip_empty) continue;
         if (d <= seg_len) {
             row_perm.push_back(r);
             continue;
@@ -128,10 +147,59 @@ int plan_rows_host(const int *ptr, int M, int seg_len, int reorder, std::vector<
     return 0;
 }
 
+static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const int *re, int skip_empty,
+                       cudaStream_t stream) {
+    Plan &p = h->plan;
+    const int M = h->num_v, K = h->feat;
+    std::vector<int> row_perm, heavy_rows, heavy_seg0;
+    std::vector<SegDesc> segs;
+    long long panel_len = 0;
+    int rc = plan_rows_host(rb, re, M, p.seg_len, (int)h->opt_reorder, skip_empty, row_perm, heavy_rows, heavy_seg0,
+                            segs, &panel_len);
+    if (rc) return rc;
+    bp.n_light = (int)row_perm.size();
+    bp.n_heavy = (int)heavy_rows.size();
+    bp.n_seg = (int)segs.size();
+    bp.panel_len = panel_len;
+
+    auto upload = [&](void **dst, const void *src, size_t bytes) -> int {
+        if (bytes == 0) return 0;
+        SB_CUDA(cudaMalloc(dst, bytes));
+        SB_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return 0;
+    };
+    std::vector<int4> light((size_t)bp.n_light);
+    for (int i = 0; i < bp.n_light; ++i) {
+        const int r = row_perm[i];
+        light[i] = make_int4(r, rb[r], re[r] - rb[r], 0);
+    }
+    std::vector<int> seg_hrow((size_t)bp.n_seg);
+    for (int hr = 0; hr < bp.n_heavy; ++hr)
+        for (int sgm = heavy_seg0[hr]; sgm < heavy_seg0[hr + 1]; ++sgm) seg_hrow[sgm] = hr;
+    if ((rc = upload((void **)&bp.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
+    if ((rc = upload((void **)&bp.d_light_desc, light.data(), sizeof(int4) * light.size()))) return rc;
+    if (bp.n_heavy > 0) {
+        if ((rc = upload((void **)&bp.d_seg_hrow, seg_hrow.data(), sizeof(int) * seg_hrow.size()))) return rc;
+        const size_t ncnt = (size_t)bp.n_heavy * p.n_slices;
+        SB_CUDA(cudaMalloc((void **)&bp.d_seg_count, sizeof(int) * ncnt));
+        SB_CUDA(cudaMemsetAsync(bp.d_seg_count, 0, sizeof(int) * ncnt, stream));
+        if ((rc = upload((void **)&bp.d_heavy_rows, heavy_rows.data(), sizeof(int) * heavy_rows.size()))) return rc;
+        if ((rc = upload((void **)&bp.d_heavy_seg0, heavy_seg0.data(), sizeof(int) * heavy_seg0.size()))) return rc;
+        if ((rc = upload((void **)&bp.d_seg_desc, segs.data(), sizeof(SegDesc) * segs.size()))) return rc;
+        SB_CUDA(cudaMalloc((void **)&bp.d_panel, sizeof(int2) * (size_t)panel_len));
+        SB_CUDA(cudaMalloc((void **)&bp.d_part, sizeof(float) * (size_t)bp.n_seg * K));
+        if ((rc = launch_build_panel(bp.d_seg_desc, bp.n_seg, h->d_idx, h->d_val, bp.d_panel, stream))) return rc;
+    }
+    SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+    return 0;
+}
+
 int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     Plan &p = h->plan;
     free_plan(p);
+    h->plan_select = 0;
     const int M = h->num_v, K = h->feat;
+    const int b_rows = h->b_rows > 0 ? h->b_rows : M;
     p.block = (int)h->opt_block;
     p.scalar = (K % 4) != 0;
     p.kslice = h->opt_kslice > 0 ? (int)h->opt_kslice : auto_kslice(M, K);
@@ -143,6 +211,9 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     p.seg_len = h->opt_seg_len > 0 ? (int)h->opt_seg_len : auto_seg_len(h->num_e, p.lanes);
     p.tune = (int)h->opt_tune;
     if (p.scalar) p.seg_len = 0x7fffffff;   // scalar fallback keeps every row whole
+    int nb = h->opt_col_blocks > 0 ? (int)h->opt_col_blocks : auto_col_blocks(b_rows, K, h->num_e, M);
+    if (p.scalar || M == 0 || nb < 1) nb = 1;
+    if (nb > b_rows) nb = b_rows > 0 ? b_rows : 1;
 
     std::vector<int> ptr((size_t)M + 1, 0);
     if (M > 0) {
@@ -155,50 +226,43 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         return SPMM_B200_EINVAL;
     }
 
-    std::vector<int> row_perm, heavy_rows, heavy_seg0;
-    std::vector<SegDesc> segs;
-    long long panel_len = 0;
-    int rc = plan_rows_host(ptr.data(), M, p.seg_len, (int)h->opt_reorder, row_perm, heavy_rows, heavy_seg0, segs,
-                            &panel_len);
-    if (rc) return rc;
-    p.n_light = (int)row_perm.size();
-    p.n_heavy = (int)heavy_rows.size();
-    p.n_seg = (int)segs.size();
-    p.panel_len = panel_len;
-
-    auto upload = [&](void **dst, const void *src, size_t bytes) -> int {
-        if (bytes == 0) return 0;
-        SB_CUDA(cudaMalloc(dst, bytes));
-        SB_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, stream));
-        return 0;
-    };
-    if ((rc = upload((void **)&p.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
-    {
-        std::vector<int4> light((size_t)p.n_light);
-        for (int i = 0; i < p.n_light; ++i) {
-            const int r = row_perm[i];
-            light[i] = make_int4(r, ptr[r], ptr[r + 1] - ptr[r], 0);
+    // split every row at the column-block boundaries (needs ascending columns inside a row; a graph
+    // that is not sorted falls back to a single block)
+    std::vector<int> split;
+    const int cols_per_block = nb > 1 ? (b_rows + nb - 1) / nb : b_rows;
+    if (nb > 1) {
+        int *d_unsorted = nullptr;
+        SB_CUDA(cudaMalloc((void **)&p.d_split, sizeof(int) * (size_t)(nb + 1) * M));
+        SB_CUDA(cudaMalloc((void **)&d_unsorted, sizeof(int)));
+        SB_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(int), stream));
+        int rc = launch_split_rows(h->d_ptr, h->d_idx, M, nb, cols_per_block, p.d_split, d_unsorted, stream);
+        int unsorted = 0;
+        cudaError_t e = cudaSuccess;
+        if (rc == 0) e = cudaMemcpyAsync(&unsorted, d_unsorted, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (rc == 0 && e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(d_unsorted);
+        if (rc) return rc;
+        SB_CUDA(e);
+        if (unsorted) {
+            cudaFree(p.d_split);
+            p.d_split = nullptr;
+            nb = 1;
+        } else {
+            split.resize((size_t)(nb + 1) * M);
+            SB_CUDA(cudaMemcpy(split.data(), p.d_split, sizeof(int) * split.size(), cudaMemcpyDeviceToHost));
         }
-        if ((rc = upload((void **)&p.d_light_desc, light.data(), sizeof(int4) * light.size()))) return rc;
-        SB_CUDA(cudaStreamSynchronize(stream));
     }
-    if (p.n_heavy > 0) {
-        std::vector<int> seg_hrow((size_t)p.n_seg);
-        for (int hr = 0; hr < p.n_heavy; ++hr)
-            for (int sgm = heavy_seg0[hr]; sgm < heavy_seg0[hr + 1]; ++sgm) seg_hrow[sgm] = hr;
-        if ((rc = upload((void **)&p.d_seg_hrow, seg_hrow.data(), sizeof(int) * seg_hrow.size()))) return rc;
-        SB_CUDA(cudaStreamSynchronize(stream));
-        const size_t ncnt = (size_t)p.n_heavy * p.n_slices;
-        SB_CUDA(cudaMalloc((void **)&p.d_seg_count, sizeof(int) * ncnt));
-        SB_CUDA(cudaMemsetAsync(p.d_seg_count, 0, sizeof(int) * ncnt, stream));
-        if ((rc = upload((void **)&p.d_heavy_rows, heavy_rows.data(), sizeof(int) * heavy_rows.size()))) return rc;
-        if ((rc = upload((void **)&p.d_heavy_seg0, heavy_seg0.data(), sizeof(int) * heavy_seg0.size()))) return rc;
-        if ((rc = upload((void **)&p.d_seg_desc, segs.data(), sizeof(SegDesc) * segs.size()))) return rc;
-        SB_CUDA(cudaMalloc((void **)&p.d_panel, sizeof(int2) * (size_t)panel_len));
-        SB_CUDA(cudaMalloc((void **)&p.d_part, sizeof(float) * (size_t)p.n_seg * K));
-        if ((rc = launch_build_panel(p.d_seg_desc, p.n_seg, h->d_idx, h->d_val, p.d_panel, stream))) return rc;
+    p.n_col_blocks = nb;
+    p.blocks.resize(nb);
+    for (int b = 0; b < nb; ++b) {
+        BlockPlan &bp = p.blocks[b];
+        bp.col_begin = nb > 1 ? b * cols_per_block : 0;
+        bp.col_end = nb > 1 ? (b + 1 == nb ? b_rows : (b + 1) * cols_per_block) : b_rows;
+        const int *rb = nb > 1 ? split.data() + (size_t)b * M : ptr.data();
+        const int *re = nb > 1 ? split.data() + (size_t)(b + 1) * M : ptr.data() + 1;
+        int rc = build_block(h, bp, rb, re, b > 0, stream);
+        if (rc) return rc;
     }
-    SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
     p.ready = true;
     return 0;
 }
@@ -222,7 +286,7 @@ extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, int feat_in, lon
     if (seg_len > 0x7fffffffll) seg_len = 0x7fffffffll;
     std::vector<int> rp, hr, hs;
     std::vector<SegDesc> segs;
-    int rc = plan_rows_host(h_ptr, num_v, (int)seg_len, reorder, rp, hr, hs, segs, panel_len);
+    int rc = plan_rows_host(h_ptr, h_ptr + 1, num_v, (int)seg_len, reorder, 0, rp, hr, hs, segs, panel_len);
     if (rc) return rc;
     *n_light = (int)rp.size();
     *n_heavy = (int)hr.size();

@@ -160,6 +160,13 @@ __device__ __forceinline__ void light_rows(const RunArgs &a, long long gw, int l
         acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         colok[v] = col0 + v * LANES * 4 < col_end;
     }
+    if (a.accumulate && row >= 0) {
+        // a later column block continues the row's chain where the previous pass left it in C
+        const float *crow = a.vout + (size_t)row * K + col0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (colok[v]) acc[v] = __ldcg(reinterpret_cast<const float4 *>(crow + v * LANES * 4));
+    }
 
     // col/val of the next LANES nonzeros are requested before the current ones are consumed, so a
     // row never waits for an index load and then again for the gathers that depend on it
@@ -325,9 +332,8 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, in
     float *crow = a.vout + (size_t)d.row * K;
     for (int col = slice * a.kslice + lane * 4; col < col_end; col += 128) {
         const float *p = a.part + (size_t)s0 * K + col;
-        float4 sum = __ldcg(reinterpret_cast<const float4 *>(p));
-        for (int sgm = s0 + 1; sgm < s1; ++sgm) {
-            p += K;
+        float4 sum = a.accumulate ? __ldcg(reinterpret_cast<const float4 *>(crow + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sgm = s0; sgm < s1; ++sgm, p += K) {
             const float4 x = __ldcg(reinterpret_cast<const float4 *>(p));
             sum.x += x.x;
             sum.y += x.y;
@@ -385,6 +391,35 @@ __global__ void __launch_bounds__(256) spmm_scalar_kernel(const RunArgs a) {
 }
 
 // ---- preprocessing / support kernels ---------------------------------------------------------
+
+// one warp per row: position of every column-block boundary inside the row (binary search by lane b),
+// and a check that the row's columns ascend (otherwise the blocks are not contiguous)
+__global__ void __launch_bounds__(256) split_rows_kernel(const int *ptr, const int *idx, int num_v, int nb,
+                                                         int cols_per_block, int *split, int *unsorted) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= num_v) return;
+    const int begin = ptr[gw], end = ptr[gw + 1];
+    bool bad = false;
+    for (int i = begin + lane; i + 1 < end; i += 32) bad |= idx[i] > idx[i + 1];
+    if (__any_sync(kFull, bad) && lane == 0) atomicExch(unsorted, 1);
+    for (int b = lane; b <= nb; b += 32) {
+        int pos;
+        if (b == 0) pos = begin;
+        else if (b == nb) pos = end;
+        else {
+            const int target = b * cols_per_block;   // first position with idx >= target
+            int lo = begin, hi = end;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (idx[mid] < target) lo = mid + 1;
+                else hi = mid;
+            }
+            pos = lo;
+        }
+        split[(size_t)b * num_v + gw] = pos;
+    }
+}
 
 // one warp per segment: gather its {col, val} pairs into the panel, zero the pad entry
 __global__ void __launch_bounds__(256) build_panel_kernel(const SegDesc *seg, int n_seg, const int *idx,
@@ -458,47 +493,62 @@ void launch_shape(const RunArgs &a, int block, int tune, cudaStream_t stream) {
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
                 int *launches) {
     const Plan &p = h->plan;
-    RunArgs a;
-    a.idx = h->d_idx;
-    a.val = h->d_val;
-    a.vin = vin;
-    a.vout = vout;
-    a.feat = h->feat;
-    a.kslice = p.kslice;
-    a.n_slices = p.n_slices;
-    a.light_desc = p.d_light_desc;
-    a.n_light = p.n_light;
-    a.seg_desc = p.d_seg_desc;
-    a.seg_hrow = p.d_seg_hrow;
-    a.seg_count = p.d_seg_count;
-    a.panel = p.d_panel;
-    a.part = p.d_part;
-    a.n_seg = p.n_seg;
-    a.heavy_seg0 = p.d_heavy_seg0;
-    a.heavy_tasks = (long long)p.n_seg * p.n_slices;
     *launches = 0;
     if (h->num_v == 0 || h->feat == 0) return 0;
-    if (p.scalar) {
-        a.light_tasks_per_slice = a.n_light;
-        const int warps = p.block / 32;
-        spmm_scalar_kernel<<<(unsigned)((a.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
-    } else {
-        const int groups = 32 / p.lanes;
-        a.light_tasks_per_slice = (a.n_light + groups - 1) / groups;
-        switch (p.lanes * 10 + p.vec) {
-            case 11: launch_shape<1, 1>(a, p.block, p.tune, stream); break;
-            case 21: launch_shape<2, 1>(a, p.block, p.tune, stream); break;
-            case 41: launch_shape<4, 1>(a, p.block, p.tune, stream); break;
-            case 81: launch_shape<8, 1>(a, p.block, p.tune, stream); break;
-            case 161: launch_shape<16, 1>(a, p.block, p.tune, stream); break;
-            case 321: launch_shape<32, 1>(a, p.block, p.tune, stream); break;
-            case 322: launch_shape<32, 2>(a, p.block, p.tune, stream); break;
-            default:
-                set_error("unsupported kernel shape lanes=%d vec=%d", p.lanes, p.vec);
-                return SPMM_B200_EINVAL;
+    for (int blk = 0; blk < p.n_col_blocks; ++blk) {
+        const BlockPlan &bp = p.blocks[blk];
+        if (blk > 0 && bp.n_light == 0 && bp.n_seg == 0) continue;
+        RunArgs a;
+        a.idx = h->d_idx;
+        a.val = h->d_val;
+        a.vin = vin;
+        a.vout = vout;
+        a.feat = h->feat;
+        a.kslice = p.kslice;
+        a.n_slices = p.n_slices;
+        a.light_desc = bp.d_light_desc;
+        a.n_light = bp.n_light;
+        a.seg_desc = bp.d_seg_desc;
+        a.seg_hrow = bp.d_seg_hrow;
+        a.seg_count = bp.d_seg_count;
+        a.panel = bp.d_panel;
+        a.part = bp.d_part;
+        a.n_seg = bp.n_seg;
+        a.heavy_seg0 = bp.d_heavy_seg0;
+        a.heavy_tasks = (long long)bp.n_seg * p.n_slices;
+        a.accumulate = blk > 0;
+        if (p.scalar) {
+            a.light_tasks_per_slice = a.n_light;
+            const int warps = p.block / 32;
+            spmm_scalar_kernel<<<(unsigned)((a.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
+        } else {
+            const int groups = 32 / p.lanes;
+            a.light_tasks_per_slice = (a.n_light + groups - 1) / groups;
+            switch (p.lanes * 10 + p.vec) {
+                case 11: launch_shape<1, 1>(a, p.block, p.tune, stream); break;
+                case 21: launch_shape<2, 1>(a, p.block, p.tune, stream); break;
+                case 41: launch_shape<4, 1>(a, p.block, p.tune, stream); break;
+                case 81: launch_shape<8, 1>(a, p.block, p.tune, stream); break;
+                case 161: launch_shape<16, 1>(a, p.block, p.tune, stream); break;
+                case 321: launch_shape<32, 1>(a, p.block, p.tune, stream); break;
+                case 322: launch_shape<32, 2>(a, p.block, p.tune, stream); break;
+                default:
+                    set_error("unsupported kernel shape lanes=%d vec=%d", p.lanes, p.vec);
+                    return SPMM_B200_EINVAL;
+            }
         }
+        ++*launches;
     }
-    ++*launches;
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
+                      int *d_split, int *d_unsorted, cudaStream_t stream) {
+    if (num_v == 0) return 0;
+    const long long threads = (long long)num_v * 32;
+    split_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_ptr, d_idx, num_v, n_col_blocks,
+                                                                            cols_per_block, d_split, d_unsorted);
     SB_CUDA(cudaGetLastError());
     return 0;
 }

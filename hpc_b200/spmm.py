@@ -119,26 +119,38 @@ class SpMMB200(SpMM):
     def launches_per_run(self) -> int:
         return lib.spmm_b200_launches_per_run(self._h)
 
-    def plan_info(self) -> dict:
+    def plan_info(self, col_block: int = 0) -> dict:
+        check(lib.spmm_b200_plan_select(self._h, col_block))
         info = PlanInfo()
         check(lib.spmm_b200_plan_info(self._h, C.byref(info)))
         return info.as_dict()
 
-    def plan_arrays(self) -> dict:
-        """The plan, copied to host numpy arrays (parity tests compare these with the oracle)."""
-        info = self.plan_info()
+    def plan_arrays(self, col_block: int = 0) -> dict:
+        """One column block's plan, copied to host numpy arrays (parity tests compare these with the oracle)."""
+        info = self.plan_info(col_block)
         out = {}
+        nb = info["n_col_blocks"]
         for which, name, n in ((0, "row_perm", info["n_light"]), (1, "heavy_rows", info["n_heavy"]),
                                (2, "heavy_seg0", info["n_heavy"] + 1 if info["n_heavy"] else 0),
                                (3, "seg_desc", info["n_seg"] * 4), (4, "panel", info["panel_len"] * 2),
-                               (5, "light_desc", info["n_light"] * 4), (6, "seg_hrow", info["n_seg"])):
+                               (5, "light_desc", info["n_light"] * 4), (6, "seg_hrow", info["n_seg"]),
+                               (7, "split", (nb + 1) * self.num_v if nb > 1 else 0)):
             a = np.empty(n, dtype=np.int32)
             check(lib.spmm_b200_plan_copy(self._h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
             out[name] = a
         out["seg_desc"] = out["seg_desc"].reshape(-1, 4)
         out["panel"] = out["panel"].reshape(-1, 2)
         out["light_desc"] = out["light_desc"].reshape(-1, 4)
+        if nb > 1:
+            out["split"] = out["split"].reshape(nb + 1, self.num_v)
         return out
+
+    def heavy_row_set(self) -> set:
+        """Rows that are split into segments in ANY column block (re-associated sums)."""
+        rows = set()
+        for b in range(self.plan_info(0)["n_col_blocks"]):
+            rows.update(self.plan_arrays(b)["heavy_rows"].tolist())
+        return rows
 
     def close(self) -> None:
         if getattr(self, "_h", None):

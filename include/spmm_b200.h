@@ -44,6 +44,9 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "kslice"    feature columns per pass over the graph (0 = auto; else multiple of 4)
  *   "block"     threads per CTA (multiple of 32)
  *   "reorder"   1 = degree-bucketed row order (default), 0 = natural order
+ *   "col_blocks" passes over A, each gathering from one band of B rows that fits the L2
+ *               (0 = auto: 1 unless B is larger than the L2 and rows are long); needs ascending
+ *               columns inside each row, otherwise falls back to 1
  *   "tune"      measured kernel variant, 0 (default) .. 3, see hpc_b200/csrc/spmm_kernels.cu
  *   "b_rows"    rows of B when A is a row block of a larger graph (0 = num_v); only
  *               spmm_b200_run_host needs it, to size its copy of B
@@ -95,7 +98,13 @@ typedef struct {
     long long panel_len; /* entries (8 bytes each) in the staged col/val panel */
     int lanes;          /* lanes cooperating on one row in the light kernel */
     int vec;            /* float4 per lane */
+    int n_col_blocks;   /* passes over A, one per band of B rows (1 = the whole matrix at once) */
+    int col_begin, col_end; /* band of B rows of the selected column block */
 } spmm_b200_plan_info_t;
+
+/* With n_col_blocks > 1 the plan holds one set of arrays per column block; plan_info / plan_copy
+ * describe the block chosen here (0 after preprocess). n_light .. panel_len are per block. */
+int spmm_b200_plan_select(spmm_b200_t h, int col_block);
 
 int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
 
@@ -107,6 +116,8 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *   4 panel      int32[panel_len*2] {col, float bits of val} pairs, segment-major
  *   5 light_desc int32[n_light*4]   {row, ptr[row], deg(row), 0} per light row, same order as row_perm
  *   6 seg_hrow   int32[n_seg]       index into heavy_rows of each segment's row
+ *   7 split      int32[(n_col_blocks+1)*num_v]  block-major: CSR position where column block b starts
+ *                                   in row r (empty when n_col_blocks == 1)
  * Returns SPMM_B200_EINVAL when `bytes` is not the exact size. */
 int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);
 

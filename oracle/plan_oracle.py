@@ -55,21 +55,55 @@ def bit_length(deg: np.ndarray) -> np.ndarray:
     return out
 
 
-def plan(ptr, idx, val, seg_len: int, reorder: bool = True) -> dict:
+def auto_col_blocks(b_rows: int, feat: int, nnz: int, num_v: int) -> int:
+    """Passes over A, one per band of B rows: 1 unless B exceeds 96 MB; then ceil(B bytes / 48 MB),
+    accepted when <= 16 and a row still averages >= 64 nonzeros per block."""
+    b_bytes = b_rows * feat * 4
+    if feat % 4 or num_v <= 0 or b_bytes <= (96 << 20):
+        return 1
+    nb = -(-b_bytes // (48 << 20))
+    if nb > 16 or nnz // num_v // nb < 64:
+        return 1
+    return nb
+
+
+def split_rows(ptr, idx, nb: int, b_rows: int) -> np.ndarray:
+    """split[b, r] = first CSR position of row r whose column is >= b * ceil(b_rows / nb)
+    (split[0] = ptr[r], split[nb] = ptr[r+1]); columns must ascend inside a row."""
+    ptr = np.asarray(ptr, np.int64)
+    idx = np.asarray(idx, np.int64)
+    m = len(ptr) - 1
+    cpb = -(-b_rows // nb)
+    # rank of (row, column) pairs in the row-major, column-ascending order the CSR already has
+    row_of = np.repeat(np.arange(m, dtype=np.int64), np.diff(ptr))
+    keys = row_of * (b_rows + 1) + idx
+    out = np.empty((nb + 1, m), np.int64)
+    out[0], out[nb] = ptr[:-1], ptr[1:]
+    for b in range(1, nb):
+        out[b] = np.searchsorted(keys, np.arange(m, dtype=np.int64) * (b_rows + 1) + b * cpb, side="left")
+    return out.astype(np.int32)
+
+
+def plan(ptr, idx, val, seg_len: int, reorder: bool = True, rb=None, re=None, skip_empty: bool = False) -> dict:
+    """Plan of the whole matrix (rb/re omitted) or of one column block (row r owns [rb[r], re[r]))."""
     ptr = np.asarray(ptr, np.int64)
     m = len(ptr) - 1
-    deg = np.diff(ptr)
+    rb = ptr[:-1] if rb is None else np.asarray(rb, np.int64)
+    re = ptr[1:] if re is None else np.asarray(re, np.int64)
+    deg = re - rb
     if reorder:
         order = np.argsort(-bit_length(deg), kind="stable")
     else:
         order = np.arange(m)
+    if skip_empty:
+        order = order[deg[order] > 0]
     heavy_mask = deg[order] > seg_len
     row_perm = order[~heavy_mask].astype(np.int32)
     heavy_rows = order[heavy_mask].astype(np.int32)
     seg_desc, heavy_seg0, panel = [], [0], []
     off = 0
     for r in heavy_rows:
-        d, begin = int(deg[r]), int(ptr[r])
+        d, begin = int(deg[r]), int(rb[r])
         nseg = -(-d // seg_len)
         for j in range(nseg):
             b = begin + j * d // nseg
@@ -83,7 +117,7 @@ def plan(ptr, idx, val, seg_len: int, reorder: bool = True) -> dict:
             panel.append(pairs)
             off += len(pairs)
         heavy_seg0.append(len(seg_desc))
-    light_desc = np.stack([row_perm.astype(np.int64), ptr[row_perm], deg[row_perm], np.zeros(len(row_perm), np.int64)],
+    light_desc = np.stack([row_perm.astype(np.int64), rb[row_perm], deg[row_perm], np.zeros(len(row_perm), np.int64)],
                           axis=1).astype(np.int32).reshape(-1, 4)
     seg_hrow = np.repeat(np.arange(len(heavy_rows)), np.diff(heavy_seg0)).astype(np.int32) if len(heavy_rows) else np.zeros(0, np.int32)
     return {

@@ -61,8 +61,8 @@ def check_against_oracle(ptr, idx, K, op, g, vin, got):
     val, b = g.val.cpu().numpy(), vin.cpu().numpy()
     ref = O.spmm_f32(ptr, idx, val, b, K)
     assert not np.isnan(got).any()
-    pa = op.plan_arrays()
-    light = pa["row_perm"]
+    heavy = op.heavy_row_set()
+    light = np.asarray([r for r in range(M) if r not in heavy], np.int64)
     assert np.array_equal(got[light].view(np.int32), ref[light].view(np.int32)), "whole rows must be bit-exact"
     ab = O.spmm_abssum(ptr, idx, val, b, K)
     assert np.all(np.abs(got.astype(np.float64) - ref) <= TOL * ab + 1e-30)
@@ -99,7 +99,8 @@ def test_engine_vs_reference_kernel(shape, K):
     ref_out = torch.zeros(M * K, device=DEV)
     refshim.ref_spmm(g.ptr, g.idx, g.val, vin, ref_out, M, g.num_e, K)
     ref = ref_out.cpu().numpy().reshape(M, K)
-    light = op.plan_arrays()["row_perm"]
+    heavy = op.heavy_row_set()
+    light = np.asarray([r for r in range(M) if r not in heavy], np.int64)
     assert np.array_equal(got[light].view(np.int32), ref[light].view(np.int32))
     # reference's own validator, reference's own argument order (test_spmm.cu:43)
     assert refshim.ref_valid(vout, ref_out, M * K) < M * K // 10000 + 1
@@ -117,6 +118,8 @@ def test_engine_vs_reference_kernel(shape, K):
     ("c0", 256, {"kslice": 128}), ("c0", 64, {}), ("c0", 128, {"block": 128}), ("c0", 512, {}), ("c0", 260, {}),
     ("c0", 100, {}), ("c0", 20, {}), ("c0", 8, {}), ("c0", 4, {}), ("c0", 30, {}), ("c0", 7, {}), ("c0", 1, {}),
     ("arxiv", 32, {}), ("arxiv", 256, {}), ("arxiv", 256, {"kslice": 32, "seg_len": 128}),
+    ("c0", 32, {"col_blocks": 3}), ("c0", 256, {"col_blocks": 4, "seg_len": 16}), ("arxiv", 256, {"col_blocks": 5}),
+    ("arxiv", 32, {"col_blocks": 2, "reorder": 0}), ("c0", 64, {"col_blocks": 64}),
     ("arxiv", 32, {"tune": 1}), ("arxiv", 256, {"tune": 2}), ("c0", 64, {"tune": 2, "seg_len": 32}), ("arxiv", 256, {"tune": 3}),
 ])
 def test_engine_matches_oracle(shape, K, opts):
@@ -271,6 +274,56 @@ def test_plan_matches_oracle(shape, seg_len, reorder):
     op.close()
 
 
+@pytest.mark.parametrize("shape,K,nb,seg_len", [("c0", 32, 3, 16), ("arxiv", 256, 4, 0), ("c0", 64, 7, 32)])
+def test_column_block_plan_matches_oracle(shape, K, nb, seg_len):
+    ptr, idx = H.gen_named_graph(shape)
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    op = H.SpMMB200(g, K, col_blocks=nb, seg_len=seg_len)
+    op.preprocess(vin, vout)
+    info = op.plan_info(0)
+    assert info["n_col_blocks"] == nb
+    M = g.num_v
+    split = P.split_rows(ptr, idx, nb, M)
+    val = g.val.cpu().numpy()
+    cpb = -(-M // nb)
+    covered = np.zeros(len(idx), np.int32)
+    for b in range(nb):
+        got = op.plan_arrays(b)
+        inf = op.plan_info(b)
+        assert (inf["col_begin"], inf["col_end"]) == (b * cpb, min(M, (b + 1) * cpb))
+        assert np.array_equal(got["split"], split)
+        want = P.plan(ptr, idx, val, inf["seg_len"], True, rb=split[b], re=split[b + 1], skip_empty=b > 0)
+        for k in ("row_perm", "light_desc", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
+            assert np.array_equal(got[k], want[k]), (b, k)
+        # every nonzero of the block lies in its band of B rows
+        for r0, beg, d, _ in got["light_desc"][:200]:
+            assert np.all((idx[beg:beg + d] >= inf["col_begin"]) & (idx[beg:beg + d] < inf["col_end"]))
+        for row, beg, d, _ in got["light_desc"]:
+            covered[beg:beg + d] += 1
+        for row, off, ln, nb0 in got["seg_desc"]:
+            covered[nb0:nb0 + ln] += 1
+    assert np.all(covered == 1)        # the blocks tile A exactly once
+    op.close()
+
+
+def test_unsorted_columns_fall_back_to_one_block():
+    rows = [[(5, 1.0), (1, 2.0), (3, 3.0)], [(2, 1.0)], [], [(0, 1.0), (7, -1.0)]] + [[] for _ in range(4)]
+    ptr, idx, val = tiny_csr(rows)
+    rng = np.random.default_rng(1)
+    b = rng.normal(0, 1, (8, 8)).astype(np.float32)
+    op, g, vin, vout, got = run_engine(ptr, idx, 8, val=val, b=b, col_blocks=2)
+    assert op.plan_info()["n_col_blocks"] == 1
+    assert np.array_equal(got.view(np.int32), O.spmm_literal(ptr, idx, val, b, 8).view(np.int32))
+    op.close()
+
+
+def test_auto_col_blocks_rule():
+    assert P.auto_col_blocks(232965, 256, 114615892, 232965) == 5       # reddit K=256: B = 239 MB
+    assert P.auto_col_blocks(232965, 32, 114615892, 232965) == 1        # B = 30 MB fits
+    assert P.auto_col_blocks(2449029, 256, 123718280, 2449029) == 1     # products: rows too short per block
+    assert P.auto_col_blocks(169343, 256, 1166243, 169343) == 1
+
+
 def test_fill_and_valid_match_oracle():
     for n, seed, stream in [(1, 123, 0), (1000, 123, 1), (1 << 20, 7, 5)]:
         t = H.fill_normal(torch.empty(n, device=DEV), seed, stream)
@@ -330,8 +383,7 @@ def _full_size_properties(shape, K):
     # (a) sampled row ranges against the oracle (bit-exact when whole, tolerance when split)
     val_h, b_h = g.val.cpu().numpy(), vin.cpu().numpy()
     deg = np.diff(ptr)
-    pa = op.plan_arrays()
-    heavy = set(pa["heavy_rows"].tolist())
+    heavy = op.heavy_row_set()
     picks = [0, M // 3, M - 64, int(np.argmax(deg)) - 3]
     for r0 in picks:
         r0 = max(0, min(M - 64, r0))

@@ -60,9 +60,9 @@ def parity(name, K, **opts):
     same_in = np.array_equal(val, O.fill_normal(len(val), 123, 1)) and np.array_equal(b, O.fill_normal(len(b), 123, 2))
     ref = O.spmm_f32(ptr, idx, val, b, K)
     info = op.plan_info()
-    pa = op.plan_arrays()
-    light = pa["row_perm"]
-    heavy = pa["heavy_rows"]
+    heavy = sorted(op.heavy_row_set())
+    hs = set(heavy)
+    light = np.asarray([r for r in range(M) if r not in hs], np.int64)
     exact_light = np.array_equal(got[light].view(np.int32), ref[light].view(np.int32))
     ab = O.spmm_abssum(ptr, idx, val, b, K)
     err = np.abs(got.astype(np.float64) - ref) / np.maximum(ab, 1e-30)
@@ -95,9 +95,10 @@ def bench(name, K, optlist, iters=10):
 
 print(torch.cuda.get_device_name(0), flush=True)
 if mode in ("quick", "full"):
-    bench("reddit", 256, [{}, {"kslice": 128}, {"kslice": 64}, {"kslice": 64, "seg_len": 128}, {"kslice": 32, "seg_len": 128},
-                          {"reorder": 0}, {"reorder": 0, "block": 32}, {"reorder": 0, "block": 64}, {"block": 64}, {"block": 128}], iters=5)
-    bench("products", 256, [{}, {"reorder": 0}, {"reorder": 0, "block": 32}, {"reorder": 0, "block": 64}, {"block": 64}, {"block": 128},
-                            {"kslice": 128}, {"kslice": 128, "reorder": 0, "block": 32}], iters=5)
-    bench("arxiv", 32, [{}, {"block": 64}, {"block": 128}, {"reorder": 0, "block": 32}])
-    bench("arxiv", 256, [{}, {"block": 64}, {"block": 128}, {"reorder": 0, "block": 32}])
+    parity("c0", 32, col_blocks=3)
+    parity("arxiv", 256, col_blocks=4)
+    bench("reddit", 256, [{"col_blocks": 1}, {"col_blocks": 2}, {"col_blocks": 3}, {"col_blocks": 4}, {}, {"col_blocks": 6},
+                          {"col_blocks": 8}, {"col_blocks": 12}, {"col_blocks": 4, "reorder": 0, "block": 32},
+                          {"col_blocks": 4, "seg_len": 128}, {"col_blocks": 4, "seg_len": 512}], iters=5)
+    bench("products", 256, [{"col_blocks": 1}, {"col_blocks": 2}, {"col_blocks": 4}, {"col_blocks": 8}], iters=5)
+    bench("reddit", 32, [{}, {"col_blocks": 2}], iters=5)
