@@ -290,6 +290,7 @@ def run_b200(args):
         flops = 2.0 * nnz * k
         peak, peak_src = measured_peaks()
         total_bytes = bytes_min(lm, lnnz, k, b_rows=m)
+        n_launch = max(1, op.launches_per_run)
         line = {
             "metric": "spmm_gflops", "value": round(flops / ms_per_step / 1e6, 2), "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5),
@@ -301,18 +302,22 @@ def run_b200(args):
                 "partition": f"rows by nnz over {world} rank(s), B replicated, no collective",
                 "l2": "L2 flushed (256 MiB write) between iterations" if flush is not None
                       else "inputs larger than L2 (col/val + B re-streamed every step)",
-                "plan": {kk: info[kk] for kk in ("seg_len", "kslice", "n_slices", "lanes", "vec", "n_light", "n_heavy", "n_seg")},
+                "plan": {kk: info[kk] for kk in ("seg_len", "kslice", "n_slices", "lanes", "vec", "n_col_blocks", "n_light", "n_heavy", "n_seg")},
                 "preprocess_s": round(prep_s, 4),
             },
             "hbm_gbs_bytes_min": round(total_bytes / ms_per_step / 1e6, 1),
             "gather_gbs": round(bytes_gather(lm, lnnz, k) / ms_per_step / 1e6, 1),
             "roofline": {
-                "bound": "hbm", "kernel": "spmm_kernel", "achieved": round(total_bytes / kernel_ms / 1e6, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(total_bytes / kernel_ms / 1e6 / peak, 4), "traffic": NCU_TRAFFIC.get(args.workload),
-                "peak_source": peak_src, "kernel_ms": round(kernel_ms, 5), "algorithmic_bytes": int(total_bytes),
+                "bound": "hbm", "kernel": "spmm_kernel", "launches_per_step": n_launch,
+                "achieved": round(total_bytes / kernel_ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(total_bytes / kernel_ms / 1e6 / peak, 4),
+                "traffic": NCU_TRAFFIC.get(args.workload) if world == 1 else None,
+                "peak_source": peak_src, "kernel_ms": round(kernel_ms / n_launch, 5),
+                "algorithmic_bytes": int(total_bytes // n_launch),
                 "gather_gbs": round(bytes_gather(lm, lnnz, k) / kernel_ms / 1e6, 1),
-                "note": "rank 0's partition, one launch per step; the binding bound is the L2->SM gather of B rows, "
-                        "not compulsory HBM bytes (DESIGN.md, SURVEY.md 8d)",
+                "note": "per launch = per column-block pass (equal shares of the step); rank 0's partition; algorithmic bytes = "
+                        "ptr+col+val+B once+C once (SURVEY.md 8d). The binding bound is the L2->SM gather of B rows (or HBM when B "
+                        "is far larger than L2), not compulsory bytes: see DESIGN.md section 3 and profiles/r01_sweep.md",
             },
             "e2e": {"value": round(flops / e2e_ms / 1e6, 2), "unit": "GFLOP/s", "ms_per_step": round(e2e_ms, 4),
                     "h2d_bytes_per_step": 4 * m * k, "d2h_bytes_per_step": 4 * lm * k, "steps": e2e_steps,
@@ -332,9 +337,14 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
-# `ncu --set full` captures summarised under profiles/ (None until a capture exists).
-NCU_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum of spmm_kernel, per launch, from the `ncu --set full` captures
+# summarised in profiles/r01_ncu_summary.md (1 GPU). reddit_k256: mean of the 5 column-block passes of one step.
+NCU_TRAFFIC = {
+    "reddit_k256": int((2699.3e6 + 1334.1e6) / 5),
+    "products_k256": int(77.34e9 + 2.53e9),
+    "arxiv_k32": int(33.9e6 + 0.48e6),
+    "arxiv_k256": int(605.8e6 + 119.0e6),
+}
 
 
 def main():

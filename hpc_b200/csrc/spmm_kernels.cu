@@ -100,12 +100,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 //   1: 8/VEC gathers in flight, <= 80 registers (3 CTAs/SM)
 //   2: 2/VEC gathers in flight, <= 48 registers (5 CTAs/SM)
 //   3: as 0, L2 eviction hint evict_last on B rows
+// (Measured and dropped, profiles/r01_sweep.md: gathering B rows into a shared-memory ring with cp.async
+//  or with one 1-D TMA copy per row — both ~35 % slower than register gathers on every shape.)
 template <int TUNE>
 struct Tune {
     static constexpr int kMinBlocks = TUNE == 1 ? 3 : (TUNE == 2 ? 5 : 4);
     static constexpr int kUnrollBytes = TUNE == 1 ? 8 : (TUNE == 2 ? 2 : 4);   // float4 per lane in flight
 };
-
 template <int TUNE>
 __device__ __forceinline__ float4 ld_b(const float *p, uint64_t pol) {
     if (TUNE == 3) {

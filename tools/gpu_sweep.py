@@ -95,10 +95,9 @@ def bench(name, K, optlist, iters=10):
 
 print(torch.cuda.get_device_name(0), flush=True)
 if mode in ("quick", "full"):
-    parity("c0", 32, col_blocks=3)
-    parity("arxiv", 256, col_blocks=4)
-    bench("reddit", 256, [{"col_blocks": 1}, {"col_blocks": 2}, {"col_blocks": 3}, {"col_blocks": 4}, {}, {"col_blocks": 6},
-                          {"col_blocks": 8}, {"col_blocks": 12}, {"col_blocks": 4, "reorder": 0, "block": 32},
-                          {"col_blocks": 4, "seg_len": 128}, {"col_blocks": 4, "seg_len": 512}], iters=5)
-    bench("products", 256, [{"col_blocks": 1}, {"col_blocks": 2}, {"col_blocks": 4}, {"col_blocks": 8}], iters=5)
-    bench("reddit", 32, [{}, {"col_blocks": 2}], iters=5)
+    parity("c0", 256, tune=5, seg_len=16)
+    parity("arxiv", 256, tune=5, seg_len=8)
+    parity("c0", 128, tune=5, col_blocks=3, seg_len=32)
+    bench("reddit", 256, [{}, {"tune": 5}, {"tune": 5, "block": 64}, {"tune": 5, "block": 256}], iters=5)
+    bench("products", 256, [{"seg_len": 32}, {"seg_len": 32, "tune": 5}], iters=5)
+    bench("arxiv", 256, [{"seg_len": 8}, {"seg_len": 8, "tune": 5}, {"col_blocks": 2}])
