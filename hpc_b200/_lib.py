@@ -21,6 +21,7 @@ class PlanInfo(C.Structure):
         ("seg_len", C.c_int), ("kslice", C.c_int), ("n_slices", C.c_int), ("block", C.c_int),
         ("n_light", C.c_int), ("n_heavy", C.c_int), ("n_seg", C.c_int),
         ("panel_len", C.c_longlong), ("lanes", C.c_int), ("vec", C.c_int),
+        ("n_ltask", C.c_int), ("lpanel_len", C.c_longlong), ("light_steps", C.c_int), ("reorder", C.c_int), ("resident_warps", C.c_int),
         ("n_col_blocks", C.c_int), ("col_begin", C.c_int), ("col_end", C.c_int),
     ]
 
@@ -49,6 +50,7 @@ SIGNATURES = {
     "spmm_b200_plan_copy": (_I, [_P, _I, _P, C.c_size_t]),
     "spmm_b200_plan_host": (_I, [_P, _I, _I, _LL, _I, _P, C.POINTER(_I), _P, C.POINTER(_I), _P, _P, C.POINTER(_I),
                                  C.POINTER(_LL)]),
+    "spmm_b200_pack_light_host": (_I, [_P, _I, _I, _I, _P, _P, C.POINTER(_I), C.POINTER(_LL)]),
     "spmm_b200_fill_normal": (_I, [_P, _LL, _U64, _U64, C.c_float, C.c_float, _P]),
     "spmm_b200_valid": (_I, [_P, _P, _LL, C.POINTER(_LL), _P]),
     "spmm_b200_gen_graph": (_I, [_I, _LL, _I, _I, _I, _I, _I, _U64, _P, _P]),

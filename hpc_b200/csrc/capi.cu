@@ -73,7 +73,8 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     else if (!strcmp(name, "kslice") && value >= 0 && value % 4 == 0) h->opt_kslice = value;
     else if (!strcmp(name, "block") && value >= 32 && value <= 256 && value % 32 == 0) h->opt_block = value;
     else if (!strcmp(name, "reorder") && (value == 0 || value == 1)) h->opt_reorder = value;
-    else if (!strcmp(name, "tune") && value >= 0 && value <= 3) h->opt_tune = value;
+    else if (!strcmp(name, "tune") && value >= 0 && value <= 1) h->opt_tune = value;
+    else if (!strcmp(name, "light_steps") && value >= 0 && value <= 65536) h->opt_light_steps = value;
     else if (!strcmp(name, "col_blocks") && value >= 0 && value <= 64) h->opt_col_blocks = value;
     else if (!strcmp(name, "b_rows") && value >= 0 && value <= 0x7fffffffll) {
         h->b_rows = (int)value;   // does not touch the plan
@@ -211,6 +212,11 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info) {
     info->panel_len = b.panel_len;
     info->lanes = p.lanes;
     info->vec = p.vec;
+    info->n_ltask = b.n_ltask;
+    info->lpanel_len = b.lpanel_len;
+    info->light_steps = b.light_steps;
+    info->resident_warps = (int)p.slots;
+    info->reorder = b.reorder;
     info->n_col_blocks = p.n_col_blocks;
     info->col_begin = b.col_begin;
     info->col_end = b.col_end;
@@ -234,6 +240,8 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
         case 4: src = p.d_panel; want = sizeof(int2) * (size_t)p.panel_len; break;
         case 5: src = p.d_light_desc; want = sizeof(int4) * (size_t)p.n_light; break;
         case 6: src = p.d_seg_hrow; want = sizeof(int) * (size_t)p.n_seg; break;
+        case 8: src = p.d_ltask; want = sizeof(int2) * (size_t)p.n_ltask; break;
+        case 9: src = p.d_lpanel; want = sizeof(int2) * (size_t)p.lpanel_len; break;
         case 7:
             src = pl.d_split;
             want = pl.n_col_blocks > 1 ? sizeof(int) * (size_t)(pl.n_col_blocks + 1) * h->num_v : 0;

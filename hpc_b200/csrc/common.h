@@ -41,9 +41,12 @@ struct RunArgs {
     int kslice;      // feature columns per pass
     int n_slices;
     // light rows
-    const int4 *light_desc;   // {row, begin, deg, 0} in processing order
+    const int4 *light_desc;   // {row, begin, deg, dst} in processing order (dst: its header's slot in lpanel)
     int n_light;
-    int light_tasks_per_slice;   // warps per slice
+    int light_tasks_per_slice;   // stream tasks per slice (= n_ltask)
+    const int2 *ltask;        // light stream tasks: {lpanel offset, steps per lane group}
+    int n_ltask;
+    const int2 *lpanel;       // light rows as a stream: header {0x80000000|row, 0}, then {col, val}..., nop = {-1, -1}
     // heavy rows
     const SegDesc *seg_desc;
     const int *seg_hrow;       // segment -> index of its row in heavy_rows
@@ -63,6 +66,12 @@ struct BlockPlan {
     long long panel_len = 0;
     int *d_row_perm = nullptr;
     int4 *d_light_desc = nullptr;
+    int2 *d_ltask = nullptr;
+    int2 *d_lpanel = nullptr;
+    int n_ltask = 0;
+    int light_steps = 0;
+    int reorder = 1;
+    long long lpanel_len = 0;
     int *d_heavy_rows = nullptr;
     int *d_heavy_seg0 = nullptr;
     SegDesc *d_seg_desc = nullptr;
@@ -74,9 +83,10 @@ struct BlockPlan {
 
 struct Plan {
     bool ready = false;
-    int seg_len = 0, kslice = 0, n_slices = 0, block = 128, lanes = 0, vec = 0, tune = 0;
+    int seg_len = 0, kslice = 0, n_slices = 0, block = 128, lanes = 0, vec = 0, tune = 0, light_steps = 0;
     bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
     int n_col_blocks = 1;
+    long long slots = 0;   // warps the device keeps resident for the chosen kernel shape
     int *d_split = nullptr;   // [(n_col_blocks+1)][num_v] start of each column block inside each row
     std::vector<BlockPlan> blocks;
     int launches = 0;
@@ -89,7 +99,7 @@ struct spmm_b200_handle {
     const int *d_idx = nullptr;
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
-    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = 1, opt_tune = 0, opt_col_blocks = 0;
+    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = 1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0;
     int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
@@ -106,14 +116,21 @@ void free_plan(Plan &p);
 // spmm_kernels.cu
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
                 int *launches);
+int resident_warps(int lanes, int vec, int tune, int block);
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
                       int *d_split, int *d_unsorted, cudaStream_t stream);
+int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, const int *d_idx, const float *d_val,
+                        int2 *d_lpanel, cudaStream_t stream);
 int launch_build_panel(const SegDesc *d_seg, int n_seg, const int *d_idx, const float *d_val,
                        int2 *d_panel, cudaStream_t stream);
 int launch_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream_id, float mean,
                        float stddev, cudaStream_t stream);
 int launch_valid(const float *d_y, const float *d_y2, long long num, unsigned long long *d_count,
                  cudaStream_t stream);
+
+// Packs light rows (costs = deg + 1 entries each, in plan order) into stream tasks of `groups` interleaved lane-group
+// lanes with about `steps` entries each; dst[i] = lpanel slot of row i's header. Returns the lpanel length.
+long long pack_light_host(const int *cost, int n, int groups, int steps, int *dst, std::vector<int2> &tasks);
 
 // lanes/vec choice for a slice width (shared by plan + launch)
 inline void shape_for_kslice(int kslice, int *lanes, int *vec) {

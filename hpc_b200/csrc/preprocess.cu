@@ -27,6 +27,8 @@ void free_plan(Plan &p) {
     for (BlockPlan &b : p.blocks) {
         cudaFree(b.d_row_perm);
         cudaFree(b.d_light_desc);
+        cudaFree(b.d_ltask);
+        cudaFree(b.d_lpanel);
         cudaFree(b.d_heavy_rows);
         cudaFree(b.d_heavy_seg0);
         cudaFree(b.d_seg_desc);
@@ -147,6 +149,63 @@ int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder
     return 0;
 }
 
+// Light rows as a stream. Rows are taken in plan order; each costs deg + 1 entries (a header carrying the row id,
+// then its nonzeros). A task has `groups` lanes (one per lane group of the warp). A row goes to the least-filled
+// lane of the current task (lowest index on ties); if that lane is non-empty and the row would take it past
+// `steps` entries, the task is closed and the row opens the next one. A task's lanes are interleaved in the
+// panel — entry j of lane g sits at off + j*groups + g — and padded with nops to the longest lane (to an even
+// length when groups == 1, so every task starts on a 16-byte boundary).
+long long pack_light_host(const int *cost, int n, int groups, int steps, int *dst, std::vector<int2> &tasks) {
+    tasks.clear();
+    std::vector<int> fill((size_t)groups, 0);
+    long long off = 0;
+    auto close_task = [&]() {
+        int mx = 0;
+        for (int x : fill) mx = std::max(mx, x);
+        if (groups == 1 && (mx & 1)) ++mx;
+        tasks.push_back(make_int2((int)off, mx));
+        off += (long long)mx * groups;
+        std::fill(fill.begin(), fill.end(), 0);
+    };
+    for (int i = 0; i < n; ++i) {
+        int g = 0;
+        for (int q = 1; q < groups; ++q)
+            if (fill[q] < fill[g]) g = q;
+        if (fill[g] > 0 && fill[g] + cost[i] > steps) {
+            close_task();
+            g = 0;
+        }
+        dst[i] = (int)(off + (long long)fill[g] * groups + g);
+        fill[g] += cost[i];
+    }
+    bool any = false;
+    for (int x : fill) any |= x > 0;
+    if (any) close_task();
+    return off;
+}
+
+// Entries per lane group and stream task: 64 per warp task, at least 16 per lane group; 128 when a full warp
+// serves each row and the block is longer than 64 waves (measured, profiles/r01_sweep.md: arxiv K=256 0.142 / 0.155 ms
+// at 64 / 128; reddit K=256 6.28 / 6.14 ms; products K=256 12.45 / 12.09 ms; K=32 shapes flat from 8 to 64). Small graphs are quantised by waves — 1.1 waves of tasks
+// take as long as 2 — so when the light rows amount to fewer than 4 waves of default-sized tasks the size is
+// chosen to fill a whole number of waves of the warps the device keeps resident (`slots`, minus the heavy
+// segments that run beside them).
+int auto_light_steps(int groups, long long total_cost, long long slots, long long heavy_tasks) {
+    int dflt = 64 / groups;
+    if (dflt < 16) dflt = 16;
+    if (slots <= 0 || total_cost <= 0) return dflt;
+    if (groups == 1 && total_cost >= 64ll * slots * 64) return 128;   // very large graphs: fewer, longer tasks
+    long long avail = slots - heavy_tasks % slots;
+    if (avail < slots / 2) avail = slots;
+    const long long per_wave = avail * groups * (long long)dflt;
+    if (total_cost >= 4 * per_wave) return dflt;
+    const long long waves = (total_cost + per_wave - 1) / per_wave;
+    long long st = (total_cost + waves * avail * groups - 1) / (waves * avail * groups);
+    st += st / 16 + 1;   // head-room: lanes are filled to within one row of the target
+    if (st < 16) st = 16;
+    return (int)(st < dflt ? st : dflt);
+}
+
 static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const int *re, int skip_empty,
                        cudaStream_t stream) {
     Plan &p = h->plan;
@@ -154,7 +213,12 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
     std::vector<int> row_perm, heavy_rows, heavy_seg0;
     std::vector<SegDesc> segs;
     long long panel_len = 0;
-    int rc = plan_rows_host(rb, re, M, p.seg_len, (int)h->opt_reorder, skip_empty, row_perm, heavy_rows, heavy_seg0,
+    // Row order: degree buckets, longest first (shortens the tail, keeps the lanes of a task balanced), or
+    // natural order (option "reorder" = 0; measured within +-3 % on the large shapes, 25-50 % slower on the
+    // one-wave arxiv shape — profiles/r01_sweep.md).
+    const int reorder = (int)h->opt_reorder;
+    bp.reorder = reorder;
+    int rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, row_perm, heavy_rows, heavy_seg0,
                             segs, &panel_len);
     if (rc) return rc;
     bp.n_light = (int)row_perm.size();
@@ -169,15 +233,44 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
         return 0;
     };
     std::vector<int4> light((size_t)bp.n_light);
+    std::vector<int> cost((size_t)bp.n_light), dst((size_t)bp.n_light);
+    std::vector<int2> ltasks;
+    const int groups = p.scalar ? 1 : 32 / p.lanes;
+    for (int i = 0; i < bp.n_light; ++i) cost[i] = re[row_perm[i]] - rb[row_perm[i]] + 1;
+    long long lpanel_len = 0;
+    if (!p.scalar) {
+        int steps = p.light_steps;
+        if (h->opt_light_steps <= 0) {
+            long long total = 0;
+            for (int c : cost) total += c;
+            steps = auto_light_steps(groups, total, p.slots, (long long)segs.size() * p.n_slices);
+            if (&bp == &p.blocks[0]) p.light_steps = steps;   // reported by plan_info (block 0)
+        }
+        bp.light_steps = steps;
+        lpanel_len = pack_light_host(cost.data(), bp.n_light, groups, steps, dst.data(), ltasks);
+        if (lpanel_len > 0x7fffffffll) {
+            set_error("light panel too large");
+            return SPMM_B200_EINVAL;
+        }
+    }
     for (int i = 0; i < bp.n_light; ++i) {
         const int r = row_perm[i];
-        light[i] = make_int4(r, rb[r], re[r] - rb[r], 0);
+        light[i] = make_int4(r, rb[r], re[r] - rb[r], p.scalar ? 0 : dst[i]);
     }
+    bp.n_ltask = (int)ltasks.size();
+    bp.lpanel_len = lpanel_len;
     std::vector<int> seg_hrow((size_t)bp.n_seg);
     for (int hr = 0; hr < bp.n_heavy; ++hr)
         for (int sgm = heavy_seg0[hr]; sgm < heavy_seg0[hr + 1]; ++sgm) seg_hrow[sgm] = hr;
     if ((rc = upload((void **)&bp.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
     if ((rc = upload((void **)&bp.d_light_desc, light.data(), sizeof(int4) * light.size()))) return rc;
+    if (bp.n_ltask > 0) {
+        if ((rc = upload((void **)&bp.d_ltask, ltasks.data(), sizeof(int2) * ltasks.size()))) return rc;
+        SB_CUDA(cudaMalloc((void **)&bp.d_lpanel, sizeof(int2) * (size_t)lpanel_len));
+        SB_CUDA(cudaMemsetAsync(bp.d_lpanel, 0xFF, sizeof(int2) * (size_t)lpanel_len, stream));   // nop entries
+        if ((rc = launch_build_lpanel(bp.d_light_desc, bp.n_light, groups, h->d_idx, h->d_val, bp.d_lpanel, stream)))
+            return rc;
+    }
     if (bp.n_heavy > 0) {
         if ((rc = upload((void **)&bp.d_seg_hrow, seg_hrow.data(), sizeof(int) * seg_hrow.size()))) return rc;
         const size_t ncnt = (size_t)bp.n_heavy * p.n_slices;
@@ -210,6 +303,8 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     if (!p.scalar && K > 0) shape_for_kslice(p.kslice, &p.lanes, &p.vec);
     p.seg_len = h->opt_seg_len > 0 ? (int)h->opt_seg_len : auto_seg_len(h->num_e, p.lanes);
     p.tune = (int)h->opt_tune;
+    p.light_steps = h->opt_light_steps > 0 ? (int)h->opt_light_steps : 0;
+    p.slots = p.scalar ? 0 : resident_warps(p.lanes, p.vec, p.tune, p.block);
     if (p.scalar) p.seg_len = 0x7fffffff;   // scalar fallback keeps every row whole
     int nb = h->opt_col_blocks > 0 ? (int)h->opt_col_blocks : auto_col_blocks(b_rows, K, h->num_e, M);
     if (p.scalar || M == 0 || nb < 1) nb = 1;
@@ -295,5 +390,23 @@ extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, int feat_in, lon
     if (heavy_rows) std::copy(hr.begin(), hr.end(), heavy_rows);
     if (heavy_seg0) std::copy(hs.begin(), hs.end(), heavy_seg0);
     if (seg_desc && !segs.empty()) memcpy(seg_desc, segs.data(), sizeof(SegDesc) * segs.size());
+    return 0;
+}
+
+// Host-only light-stream packing (declared in include/spmm_b200.h).
+extern "C" int spmm_b200_pack_light_host(const int *cost, int n, int groups, int steps, int *dst, int *ltask,
+                                         int *n_ltask, long long *lpanel_len) {
+    using namespace spmm_b200;
+    if (n < 0 || groups < 1 || groups > 32 || (groups & (groups - 1)) || steps < 1 || !n_ltask || !lpanel_len ||
+        (n > 0 && !cost)) {
+        set_error("spmm_b200_pack_light_host: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    std::vector<int> d((size_t)n);
+    std::vector<int2> tasks;
+    *lpanel_len = pack_light_host(cost, n, groups, steps, d.data(), tasks);
+    *n_ltask = (int)tasks.size();
+    if (dst) std::copy(d.begin(), d.end(), dst);
+    if (ltask && !tasks.empty()) memcpy(ltask, tasks.data(), sizeof(int2) * tasks.size());
     return 0;
 }

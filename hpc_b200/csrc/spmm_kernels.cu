@@ -4,18 +4,19 @@
 // K and over the row) and the student's SpmmOptKernel (PA4/workspace/src/spmm_opt.cu:9-35:
 // one CTA per <=256-nnz task, atomicAdd into a pre-zeroed vout).
 //
-//   spmm_light_kernel  rows kept whole. LANES lanes cooperate on one row, each owning VEC
-//                      float4 of the feature slice, so a warp covers 32/LANES rows at once.
-//                      col/val are read coalesced, LANES at a time, and broadcast by shuffle;
-//                      B rows are gathered with 128-bit loads; every output element is one
-//                      in-order FMA chain from 0.0f — the same chain as spmm_ref.cu:10-14, so
-//                      the result is bit-identical to the reference for these rows.
-//   spmm_heavy_kernel  rows split into nnz-balanced segments (one warp per segment). The
-//                      segment's {col,val} panel is staged into shared memory with 1-D TMA
-//                      (cp.async.bulk + mbarrier, double buffered); the 32/LANES lane groups
-//                      take alternate nonzeros and are combined by warp shuffles.
-//   spmm_fixup_kernel  adds a heavy row's segment partials in segment order (deterministic,
-//                      no atomics, vout never needs pre-zeroing).
+//   spmm_kernel        one launch per column block. Warp tasks: heavy segments first, then light-row stream tasks.
+//     light stream     rows kept whole are packed (header + {col,val} entries) into a stream panel cut into
+//                      equal-sized warp tasks; LANES lanes cooperate on one row, each owning VEC float4 of the
+//                      feature slice, so a warp walks 32/LANES interleaved lanes of rows at once. The task's
+//                      panel is staged into shared memory with 1-D TMA (cp.async.bulk + mbarrier, double
+//                      buffered); B rows are gathered with 128-bit loads that stay in flight across row
+//                      boundaries; every output element is one in-order FMA chain from 0.0f in CSR order — the
+//                      same chain as spmm_ref.cu:10-14 — so these rows are bit-identical to the reference.
+//     heavy segments   rows longer than seg_len are cut into nnz-balanced segments (one warp each), staged the
+//                      same way; the 32/LANES lane groups take alternate nonzeros and are combined by warp
+//                      shuffles; the warp finishing a row's last segment adds the partial rows in segment
+//                      order (deterministic, no float atomics, vout never needs pre-zeroing).
+//   spmm_scalar_kernel K % 4 != 0 fallback: warp per row, scalar lanes over the columns, same chain.
 //
 // fp32 CUDA cores only: SpMM is a gather, not a dense contraction.
 #include <stdio.h>
@@ -95,131 +96,141 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // rows in plan order; a warp picks its path from its global index, so the tail of the heavy
 // segments overlaps the start of the light rows and nothing waits on a second launch.
 //
-// TUNE selects a measured variant (option "tune"; profiles/r01_sweep.md):
-//   0: 4/VEC gathers in flight per lane group, <= 64 registers (4 CTAs of 256 threads per SM)
+// TUNE selects the gathers kept in flight per lane group and the register cap (option "tune";
+// measurements in profiles/r01_sweep.md):
+//   0: 4/VEC gathers in flight, <= 64 registers (4 CTAs of 256 threads per SM)      [default]
 //   1: 8/VEC gathers in flight, <= 80 registers (3 CTAs/SM)
-//   2: 2/VEC gathers in flight, <= 48 registers (5 CTAs/SM)
-//   3: as 0, L2 eviction hint evict_last on B rows
-// (Measured and dropped, profiles/r01_sweep.md: gathering B rows into a shared-memory ring with cp.async
-//  or with one 1-D TMA copy per row — both ~35 % slower than register gathers on every shape.)
+// Measured and dropped: 2/VEC at 48 registers (spills); L1::no_allocate or L2::evict_last on B rows;
+// gathering B rows into a shared-memory ring with cp.async or with one 1-D TMA copy per row (both ~35 %
+// slower than register gathers on every shape).
+// FULL: every lane's columns are inside the slice (K a multiple of the slice width): no column predicates.
 template <int TUNE>
 struct Tune {
-    static constexpr int kMinBlocks = TUNE == 1 ? 3 : (TUNE == 2 ? 5 : 4);
-    static constexpr int kUnrollBytes = TUNE == 1 ? 8 : (TUNE == 2 ? 2 : 4);   // float4 per lane in flight
+    static constexpr int kMinBlocks = TUNE == 1 ? 3 : 4;
+    static constexpr int kUnrollBytes = TUNE == 1 ? 8 : 4;   // float4 per lane in flight
 };
-template <int TUNE>
-__device__ __forceinline__ float4 ld_b(const float *p, uint64_t pol) {
-    if (TUNE == 3) {
-        float4 r;
-        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
-        return r;
-    } else {
-        return ld_b_row(p);
-    }
-}
-template <int TUNE>
-__device__ __forceinline__ uint64_t b_policy() {
-    uint64_t pol = 0;
-    if (TUNE == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
 
-template <int LANES, int VEC, int TUNE>
-__device__ __forceinline__ void light_rows(const RunArgs &a, long long gw, int lane) {
+// Light rows as a stream: a warp walks one task of the light panel, staged through shared
+// memory by 1-D TMA exactly like a heavy segment. Lane group g reads entries g, g+GROUPS, ... of the task:
+// a header starts a new row (the previous row's accumulator is stored first), a nonzero is one B-row gather
+// and one in-order FMA, a nop is padding. Rows never span lane groups, so every row is still one FMA chain in
+// CSR order (bit-exact), but gathers stay in flight across row boundaries and no load depends on a
+// per-row descriptor.
+template <int LANES, int VEC, int TUNE, bool FULL>
+__device__ __forceinline__ void light_stream(const RunArgs &a, long long gw, int lane, int2 *buf, uint64_t *bars) {
     constexpr int GROUPS = 32 / LANES;
-    constexpr int UMAX = Tune<TUNE>::kUnrollBytes / VEC;
-    constexpr int U = LANES < UMAX ? LANES : UMAX;
-    static_assert(LANES % U == 0, "unroll must tile the chunk");
+    constexpr int U = Tune<TUNE>::kUnrollBytes / VEC < 1 ? 1 : Tune<TUNE>::kUnrollBytes / VEC;
     const int l = lane % LANES;
     const int g = lane / LANES;
-    const int slice = (int)(gw / a.light_tasks_per_slice);
+    const int slice = (int)(gw / a.n_ltask);
     if (slice >= a.n_slices) return;
-    const int task = (int)(gw - (long long)slice * a.light_tasks_per_slice);
-    const int slot = task * GROUPS + g;
+    const int task = (int)(gw - (long long)slice * a.n_ltask);
+    const int2 td = __ldg(a.ltask + task);
+    const int len = td.y * GROUPS;
+    const int nchunks = (len + kChunk - 1) / kChunk;
+    const int2 *src = a.lpanel + td.x;
 
-    int row = -1, begin = 0, deg = 0;
-    if (slot < a.n_light) {
-        const int4 d = __ldg(a.light_desc + slot);   // {row, begin, deg, 0}: one load instead of perm -> ptr
-        row = d.x;
-        begin = d.y;
-        deg = d.z;
-    }
-    int maxdeg = deg;
+    if (lane == 0) {
 #pragma unroll
-    for (int off = LANES; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(kFull, maxdeg, off));
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int k) {
+        const int s = k % kStages;
+        const uint32_t bytes = (uint32_t)min(kChunk, len - k * kChunk) * 8u;   // len is even
+        mbar_expect_tx(&bars[s], bytes);
+        tma_bulk_g2s(buf + s * kChunk, src + (size_t)k * kChunk, bytes, &bars[s]);
+    };
+    if (lane == 0) {
+        issue(0);
+        if (nchunks > 1) issue(1);
+    }
 
     const int K = a.feat;
     const int col0 = slice * a.kslice + l * 4;
     const int col_end = min(K, (slice + 1) * a.kslice);
     const float *bbase = a.vin + col0;
-    const uint64_t pol = b_policy<TUNE>();
     float4 acc[VEC];
     bool colok[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        colok[v] = col0 + v * LANES * 4 < col_end;
+        colok[v] = FULL || col0 + v * LANES * 4 < col_end;
     }
-    if (a.accumulate && row >= 0) {
-        // a later column block continues the row's chain where the previous pass left it in C
-        const float *crow = a.vout + (size_t)row * K + col0;
+    int cur_row = -1;
+    auto flush_row = [&]() {
+        if (cur_row >= 0) {
+            float *crow = a.vout + (size_t)cur_row * K + col0;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-            if (colok[v]) acc[v] = __ldcg(reinterpret_cast<const float4 *>(crow + v * LANES * 4));
-    }
+            for (int v = 0; v < VEC; ++v)
+                if (colok[v]) st_c_row(crow + v * LANES * 4, acc[v]);
+        }
+    };
 
-    // col/val of the next LANES nonzeros are requested before the current ones are consumed, so a
-    // row never waits for an index load and then again for the gathers that depend on it
-    int c = 0;
-    float w = 0.f;
-    if (l < deg) {
-        c = ld_stream_s32(a.idx + begin + l);
-        w = ld_stream_f32(a.val + begin + l);
-    }
-    for (int base = 0; base < maxdeg; base += LANES) {
-        int cn = 0;
-        float wn = 0.f;
-        const int in = base + LANES + l;
-        if (in < deg) {
-            cn = ld_stream_s32(a.idx + begin + in);
-            wn = ld_stream_f32(a.val + begin + in);
-        }
-        const int n = min(LANES, maxdeg - base);   // warp-uniform
-        for (int t0 = 0; t0 < n; t0 += U) {
+    for (int k = 0; k < nchunks; ++k) {
+        const int s = k % kStages;
+        mbar_wait(&bars[s], (uint32_t)(k / kStages) & 1u);
+        const int n = min(kChunk, len - k * kChunk);
+        const int2 *e = buf + s * kChunk;
+        for (int t0 = 0; t0 < n; t0 += GROUPS * U) {
             float4 b[U][VEC];
-            float wt[U];
-            bool ok[U];
+            int2 cv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int t = t0 + u;
-                const int ct = __shfl_sync(kFull, c, t, LANES);
-                wt[u] = __shfl_sync(kFull, w, t, LANES);
-                ok[u] = base + t < deg;
-                const float *brow = bbase + (size_t)ct * K;
+                const int t = t0 + u * GROUPS + g;
+                cv[u] = make_int2(-1, 0);
+                if (t < n) cv[u] = e[t];
+                if (cv[u].x >= 0) {
+                    const float *brow = bbase + (size_t)cv[u].x * K;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) b[u][v] = ld_b<TUNE>(brow + v * LANES * 4, pol);
+                    for (int v = 0; v < VEC; ++v)
+                        if (colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
+                }
             }
+            bool hdr = false;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < U; ++u) hdr |= cv[u].x < -1;   // headers are 0x80000000 | row; nop is -1
+            if (!__any_sync(kFull, hdr)) {
+                // common case for long rows: nonzeros (and padding) only — straight-line predicated FMAs
 #pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) fma4(acc[v], b[u][v], wt[u]);   // in CSR order: bit-exact chain
+                for (int u = 0; u < U; ++u) {
+                    const float w = __int_as_float(cv[u].y);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        if (cv[u].x >= 0 && colok[v]) fma4(acc[v], b[u][v], w);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (cv[u].x >= 0) {
+                        const float w = __int_as_float(cv[u].y);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+                            if (colok[v]) fma4(acc[v], b[u][v], w);   // CSR order within the row: bit-exact chain
+                    } else if (cv[u].x != -1) {
+                        flush_row();   // header: the previous row of this lane group is complete
+                        cur_row = cv[u].x & 0x7fffffff;
+                        if (a.accumulate) {
+                            const float *crow = a.vout + (size_t)cur_row * K + col0;
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v)
+                                if (colok[v]) acc[v] = __ldcg(reinterpret_cast<const float4 *>(crow + v * LANES * 4));
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
             }
         }
-        c = cn;
-        w = wn;
+        __syncwarp();   // every lane is done reading stage s before it is refilled
+        if (lane == 0 && k + kStages < nchunks) issue(k + kStages);
     }
-    if (row >= 0) {
-        float *crow = a.vout + (size_t)row * K + col0;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-            if (colok[v]) st_c_row(crow + v * LANES * 4, acc[v]);
-    }
+    flush_row();
 }
 
-template <int LANES, int VEC, int TUNE>
+template <int LANES, int VEC, int TUNE, bool FULL>
 __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, int lane, int2 *buf, uint64_t *bars) {
     constexpr int GROUPS = 32 / LANES;
     constexpr int U = Tune<TUNE>::kUnrollBytes / VEC;
@@ -253,13 +264,12 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, in
     const int col0 = slice * a.kslice + l * 4;
     const int col_end = min(K, (slice + 1) * a.kslice);
     const float *bbase = a.vin + col0;
-    const uint64_t pol = b_policy<TUNE>();
     float4 acc[VEC];
     bool colok[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        colok[v] = col0 + v * LANES * 4 < col_end;
+        colok[v] = FULL || col0 + v * LANES * 4 < col_end;
     }
 
     for (int k = 0; k < nchunks; ++k) {
@@ -281,7 +291,7 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, in
                 const float *brow = bbase + (size_t)cv.x * K;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) b[u][v] = ld_b<TUNE>(brow + v * LANES * 4, pol);
+                    if (ok[u] && colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -345,7 +355,7 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, in
     }
 }
 
-template <int LANES, int VEC, int TUNE>
+template <int LANES, int VEC, int TUNE, bool FULL>
 __global__ void __launch_bounds__(256, Tune<TUNE>::kMinBlocks) spmm_kernel(const RunArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -356,9 +366,12 @@ __global__ void __launch_bounds__(256, Tune<TUNE>::kMinBlocks) spmm_kernel(const
         int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
         uint64_t *bars =
             reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages;
-        heavy_segment<LANES, VEC, TUNE>(a, gw, lane, buf, bars);
+        heavy_segment<LANES, VEC, TUNE, FULL>(a, gw, lane, buf, bars);
     } else {
-        light_rows<LANES, VEC, TUNE>(a, gw - a.heavy_tasks, lane);
+        int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
+        uint64_t *bars =
+            reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages;
+        light_stream<LANES, VEC, TUNE, FULL>(a, gw - a.heavy_tasks, lane, buf, bars);
     }
 }
 
@@ -422,6 +435,18 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const int *ptr, const i
     }
 }
 
+// one warp per light row: header at its slot, nonzeros at stride `groups` after it (the panel was preset to nops)
+__global__ void __launch_bounds__(256) build_lpanel_kernel(const int4 *light_desc, int n_light, int groups, const int *idx,
+                                                           const float *val, int2 *lpanel) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_light) return;
+    const int4 d = light_desc[gw];   // {row, begin, deg, dst}
+    if (lane == 0) lpanel[d.w] = make_int2((int)(0x80000000u | (unsigned)d.x), 0);
+    for (int t = lane; t < d.z; t += 32)
+        lpanel[(size_t)d.w + (size_t)(1 + t) * groups] = make_int2(idx[d.y + t], __float_as_int(val[d.y + t]));
+}
+
 // one warp per segment: gather its {col, val} pairs into the panel, zero the pad entry
 __global__ void __launch_bounds__(256) build_panel_kernel(const SegDesc *seg, int n_seg, const int *idx,
                                                           const float *val, int2 *panel) {
@@ -473,20 +498,37 @@ __global__ void __launch_bounds__(256) valid_kernel(const float *y, const float 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
 }
 
-template <int LANES, int VEC, int TUNE>
+template <int LANES, int VEC, int TUNE, bool FULL>
 void launch_tuned(const RunArgs &a, int block, cudaStream_t stream) {
     const int warps = block / 32;
     const long long tasks = a.heavy_tasks + (long long)a.light_tasks_per_slice * a.n_slices;
     const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
-    spmm_kernel<LANES, VEC, TUNE><<<(unsigned)((tasks + warps - 1) / warps), block, smem, stream>>>(a);
+    spmm_kernel<LANES, VEC, TUNE, FULL><<<(unsigned)((tasks + warps - 1) / warps), block, smem, stream>>>(a);
 }
 
 template <int LANES, int VEC>
-void launch_shape(const RunArgs &a, int block, int tune, cudaStream_t stream) {
-    if (tune == 1) launch_tuned<LANES, VEC, 1>(a, block, stream);
-    else if (tune == 2) launch_tuned<LANES, VEC, 2>(a, block, stream);
-    else if (tune == 3) launch_tuned<LANES, VEC, 3>(a, block, stream);
-    else launch_tuned<LANES, VEC, 0>(a, block, stream);
+void launch_shape(const RunArgs &a, int block, int tune, bool full, cudaStream_t stream) {
+    if (tune == 1) {
+        if (full) launch_tuned<LANES, VEC, 1, true>(a, block, stream);
+        else launch_tuned<LANES, VEC, 1, false>(a, block, stream);
+    } else {
+        if (full) launch_tuned<LANES, VEC, 0, true>(a, block, stream);
+        else launch_tuned<LANES, VEC, 0, false>(a, block, stream);
+    }
+}
+
+template <int LANES, int VEC>
+int slots_shape(int block, int tune) {
+    int nb = 0;
+    const int warps = block / 32;
+    const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
+    cudaError_t e = tune == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_kernel<LANES, VEC, 1, true>, block, smem)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_kernel<LANES, VEC, 0, true>, block, smem);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb * warps;
 }
 
 }  // namespace
@@ -509,6 +551,9 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         a.n_slices = p.n_slices;
         a.light_desc = bp.d_light_desc;
         a.n_light = bp.n_light;
+        a.ltask = bp.d_ltask;
+        a.lpanel = bp.d_lpanel;
+        a.n_ltask = bp.n_ltask;
         a.seg_desc = bp.d_seg_desc;
         a.seg_hrow = bp.d_seg_hrow;
         a.seg_count = bp.d_seg_count;
@@ -523,16 +568,16 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
             const int warps = p.block / 32;
             spmm_scalar_kernel<<<(unsigned)((a.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
         } else {
-            const int groups = 32 / p.lanes;
-            a.light_tasks_per_slice = (a.n_light + groups - 1) / groups;
+            const bool full = h->feat % (p.lanes * p.vec * 4) == 0 && p.kslice == p.lanes * p.vec * 4;
+            a.light_tasks_per_slice = a.n_ltask;
             switch (p.lanes * 10 + p.vec) {
-                case 11: launch_shape<1, 1>(a, p.block, p.tune, stream); break;
-                case 21: launch_shape<2, 1>(a, p.block, p.tune, stream); break;
-                case 41: launch_shape<4, 1>(a, p.block, p.tune, stream); break;
-                case 81: launch_shape<8, 1>(a, p.block, p.tune, stream); break;
-                case 161: launch_shape<16, 1>(a, p.block, p.tune, stream); break;
-                case 321: launch_shape<32, 1>(a, p.block, p.tune, stream); break;
-                case 322: launch_shape<32, 2>(a, p.block, p.tune, stream); break;
+                case 11: launch_shape<1, 1>(a, p.block, p.tune, full, stream); break;
+                case 21: launch_shape<2, 1>(a, p.block, p.tune, full, stream); break;
+                case 41: launch_shape<4, 1>(a, p.block, p.tune, full, stream); break;
+                case 81: launch_shape<8, 1>(a, p.block, p.tune, full, stream); break;
+                case 161: launch_shape<16, 1>(a, p.block, p.tune, full, stream); break;
+                case 321: launch_shape<32, 1>(a, p.block, p.tune, full, stream); break;
+                case 322: launch_shape<32, 2>(a, p.block, p.tune, full, stream); break;
                 default:
                     set_error("unsupported kernel shape lanes=%d vec=%d", p.lanes, p.vec);
                     return SPMM_B200_EINVAL;
@@ -544,12 +589,43 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
     return 0;
 }
 
+// warps the device keeps resident for this kernel shape (0 when it cannot be queried, e.g. no device)
+int resident_warps(int lanes, int vec, int tune, int block) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    switch (lanes * 10 + vec) {
+        case 11: per_sm = slots_shape<1, 1>(block, tune); break;
+        case 21: per_sm = slots_shape<2, 1>(block, tune); break;
+        case 41: per_sm = slots_shape<4, 1>(block, tune); break;
+        case 81: per_sm = slots_shape<8, 1>(block, tune); break;
+        case 161: per_sm = slots_shape<16, 1>(block, tune); break;
+        case 321: per_sm = slots_shape<32, 1>(block, tune); break;
+        case 322: per_sm = slots_shape<32, 2>(block, tune); break;
+        default: break;
+    }
+    return per_sm * sms;
+}
+
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
                       int *d_split, int *d_unsorted, cudaStream_t stream) {
     if (num_v == 0) return 0;
     const long long threads = (long long)num_v * 32;
     split_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_ptr, d_idx, num_v, n_col_blocks,
                                                                             cols_per_block, d_split, d_unsorted);
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, const int *d_idx, const float *d_val,
+                        int2 *d_lpanel, cudaStream_t stream) {
+    if (n_light == 0) return 0;
+    const long long threads = (long long)n_light * 32;
+    build_lpanel_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_light_desc, n_light, groups, d_idx,
+                                                                              d_val, d_lpanel);
     SB_CUDA(cudaGetLastError());
     return 0;
 }

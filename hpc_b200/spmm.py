@@ -134,13 +134,16 @@ class SpMMB200(SpMM):
                                (2, "heavy_seg0", info["n_heavy"] + 1 if info["n_heavy"] else 0),
                                (3, "seg_desc", info["n_seg"] * 4), (4, "panel", info["panel_len"] * 2),
                                (5, "light_desc", info["n_light"] * 4), (6, "seg_hrow", info["n_seg"]),
-                               (7, "split", (nb + 1) * self.num_v if nb > 1 else 0)):
+                               (7, "split", (nb + 1) * self.num_v if nb > 1 else 0),
+                               (8, "ltask", info["n_ltask"] * 2), (9, "lpanel", info["lpanel_len"] * 2)):
             a = np.empty(n, dtype=np.int32)
             check(lib.spmm_b200_plan_copy(self._h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
             out[name] = a
         out["seg_desc"] = out["seg_desc"].reshape(-1, 4)
         out["panel"] = out["panel"].reshape(-1, 2)
         out["light_desc"] = out["light_desc"].reshape(-1, 4)
+        out["ltask"] = out["ltask"].reshape(-1, 2)
+        out["lpanel"] = out["lpanel"].reshape(-1, 2)
         if nb > 1:
             out["split"] = out["split"].reshape(nb + 1, self.num_v)
         return out
@@ -205,3 +208,17 @@ def plan_host(ptr: np.ndarray, feat: int, seg_len: int = 0, reorder: bool = True
                                   vp(seg_desc), C.byref(ns), C.byref(pl)))
     return {"row_perm": row_perm, "heavy_rows": heavy_rows, "heavy_seg0": heavy_seg0,
             "seg_desc": seg_desc.reshape(-1, 4), "panel_len": pl.value}
+
+
+def pack_light_host(cost: np.ndarray, groups: int, steps: int):
+    """The light-stream packing rule on the host (spmm_b200_pack_light_host). -> (dst, ltask[n,2], lpanel_len)"""
+    cost = np.ascontiguousarray(cost, dtype=np.int32)
+    n = len(cost)
+    nt, pl = C.c_int(0), C.c_longlong(0)
+    cp = C.c_void_p(cost.ctypes.data) if n else None
+    check(lib.spmm_b200_pack_light_host(cp, n, groups, steps, None, None, C.byref(nt), C.byref(pl)))
+    dst = np.empty(n, np.int32)
+    ltask = np.empty(nt.value * 2, np.int32)
+    check(lib.spmm_b200_pack_light_host(cp, n, groups, steps, C.c_void_p(dst.ctypes.data) if n else None,
+                                        C.c_void_p(ltask.ctypes.data) if nt.value else None, C.byref(nt), C.byref(pl)))
+    return dst, ltask.reshape(-1, 2), pl.value

@@ -44,6 +44,9 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "kslice"    feature columns per pass over the graph (0 = auto; else multiple of 4)
  *   "block"     threads per CTA (multiple of 32)
  *   "reorder"   1 = degree-bucketed row order (default), 0 = natural order
+ *   "light_steps" entries per lane group and stream task (0 = auto: 64 / groups, at least 16;
+ *               128 on very large graphs at K >= 128; smaller on graphs of fewer than 4 waves of tasks, to
+ *               fill whole waves of resident warps)
  *   "col_blocks" passes over A, each gathering from one band of B rows that fits the L2
  *               (0 = auto: 1 unless B is larger than the L2 and rows are long); needs ascending
  *               columns inside each row, otherwise falls back to 1
@@ -98,6 +101,11 @@ typedef struct {
     long long panel_len; /* entries (8 bytes each) in the staged col/val panel */
     int lanes;          /* lanes cooperating on one row in the light kernel */
     int vec;            /* float4 per lane */
+    int n_ltask;        /* light-stream tasks (one warp each) */
+    long long lpanel_len; /* entries in the light stream panel */
+    int light_steps;    /* target entries per lane group and task (selected block) */
+    int reorder;        /* row order in effect for the selected block: 1 bucketed, 0 natural */
+    int resident_warps; /* warps the device keeps resident for the kernel shape (sizes small graphs' tasks) */
     int n_col_blocks;   /* passes over A, one per band of B rows (1 = the whole matrix at once) */
     int col_begin, col_end; /* band of B rows of the selected column block */
 } spmm_b200_plan_info_t;
@@ -114,7 +122,12 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *   2 heavy_seg0 int32[n_heavy+1]   first segment of each heavy row (prefix)
  *   3 seg_desc   int32[n_seg*4]     {row, panel_off, len, nnz_begin} per segment
  *   4 panel      int32[panel_len*2] {col, float bits of val} pairs, segment-major
- *   5 light_desc int32[n_light*4]   {row, ptr[row], deg(row), 0} per light row, same order as row_perm
+ *   5 light_desc int32[n_light*4]   {row, first CSR position, nonzeros, slot of its header in lpanel} per light
+ *                                   row, same order as row_perm
+ *   8 ltask      int32[n_ltask*2]   {lpanel offset, steps per lane group} per light-stream task
+ *   9 lpanel     int32[lpanel_len*2] light rows as a stream of {x, y} entries: header {0x80000000|row, 0},
+ *                                   nonzero {col, float bits of val}, nop {-1, -1}; within a task, entry j of
+ *                                   lane group g sits at offset + j*groups + g
  *   6 seg_hrow   int32[n_seg]       index into heavy_rows of each segment's row
  *   7 split      int32[(n_col_blocks+1)*num_v]  block-major: CSR position where column block b starts
  *                                   in row r (empty when n_col_blocks == 1)
@@ -129,6 +142,12 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);
 int spmm_b200_plan_host(const int *h_ptr, int num_v, int feat_in, long long seg_len, int reorder, int *row_perm,
                         int *n_light, int *heavy_rows, int *n_heavy, int *heavy_seg0, int *seg_desc,
                         int *n_seg, long long *panel_len);
+
+/* The light-stream packing rule on the host (tests): cost[i] = nonzeros + 1 of the i-th light row in plan order;
+ * dst int32[n] receives each row's header slot, ltask int32[2*n_ltask] the tasks (call with ltask = dst = NULL
+ * first to get n_ltask / lpanel_len). groups = 32 / lanes. */
+int spmm_b200_pack_light_host(const int *cost, int n, int groups, int steps, int *dst, int *ltask, int *n_ltask,
+                              long long *lpanel_len);
 
 /* ---- support (device pointers) ------------------------------------------------------------ */
 

@@ -131,6 +131,72 @@ def plan(ptr, idx, val, seg_len: int, reorder: bool = True, rb=None, re=None, sk
     }
 
 
+def auto_light_steps(groups: int, total_cost: int, slots: int, heavy_tasks: int) -> int:
+    """Default max(16, 64 // groups); graphs of fewer than 4 waves of such tasks get a size that fills a whole
+    number of waves of the `slots` resident warps (less the heavy segments running beside them)."""
+    dflt = max(16, 64 // groups)
+    if slots <= 0 or total_cost <= 0:
+        return dflt
+    if groups == 1 and total_cost >= 64 * slots * 64:
+        return 128
+    avail = slots - heavy_tasks % slots
+    if avail < slots // 2:
+        avail = slots
+    per_wave = avail * groups * dflt
+    if total_cost >= 4 * per_wave:
+        return dflt
+    waves = -(-total_cost // per_wave)
+    st = -(-total_cost // (waves * avail * groups))
+    st += st // 16 + 1
+    return min(max(st, 16), dflt)
+
+
+def pack_light(cost, groups: int, steps: int):
+    """Light-stream packing. cost[i] = nonzeros + 1 of the i-th light row in plan order. A row goes to the
+    least-filled lane of the current task (lowest index on ties); when that lane is non-empty and would exceed
+    `steps`, the task is closed first. -> (dst slots, tasks [(offset, steps)], panel length)"""
+    dst, tasks = [], []
+    fill = [0] * groups
+    off = 0
+
+    def close():
+        nonlocal off, fill
+        mx = max(fill)
+        if groups == 1 and mx % 2:
+            mx += 1
+        tasks.append((off, mx))
+        off += mx * groups
+        fill = [0] * groups
+
+    for c in (int(x) for x in cost):
+        g = fill.index(min(fill))
+        if fill[g] > 0 and fill[g] + c > steps:
+            close()
+            g = 0
+        dst.append(off + fill[g] * groups + g)
+        fill[g] += c
+    if any(fill):
+        close()
+    return np.asarray(dst, np.int32), np.asarray(tasks, np.int32).reshape(-1, 2), off
+
+
+def light_stream(plan_dict, idx, val, groups: int, steps: int) -> dict:
+    """light_desc with header slots, task list and the stream panel for a plan() result."""
+    ld = plan_dict["light_desc"].copy()
+    dst, tasks, length = pack_light(ld[:, 2].astype(np.int64) + 1, groups, steps)
+    ld[:, 3] = dst
+    panel = np.full((length, 2), -1, np.int32)
+    idx = np.asarray(idx, np.int32)
+    bits = np.asarray(val, np.float32).view(np.int32)
+    for row, begin, deg, d in ld:
+        panel[d] = (np.uint32(0x80000000 | int(row)).astype(np.int32), 0)   # header
+        if deg:
+            sl = d + (1 + np.arange(deg)) * groups
+            panel[sl, 0] = idx[begin:begin + deg]
+            panel[sl, 1] = bits[begin:begin + deg]
+    return {"light_desc": ld, "ltask": tasks, "lpanel": panel}
+
+
 def student_split_check(ptr, tasks) -> bool:
     """With seg_len = 256 a row of deg d yields ceil(d/256) pieces in both schemes
     (spmm_opt.cu:46 steps by kBatchSize; the plan balances the same number of pieces)."""

@@ -118,9 +118,12 @@ def test_engine_vs_reference_kernel(shape, K):
     ("c0", 256, {"kslice": 128}), ("c0", 64, {}), ("c0", 128, {"block": 128}), ("c0", 512, {}), ("c0", 260, {}),
     ("c0", 100, {}), ("c0", 20, {}), ("c0", 8, {}), ("c0", 4, {}), ("c0", 30, {}), ("c0", 7, {}), ("c0", 1, {}),
     ("arxiv", 32, {}), ("arxiv", 256, {}), ("arxiv", 256, {"kslice": 32, "seg_len": 128}),
+    ("c0", 32, {"light_steps": 32}), ("c0", 64, {"light_steps": 1000}), ("arxiv", 32, {"light_steps": 33, "reorder": 0}),
+    ("c0", 8, {"light_steps": 40}), ("c0", 4, {"col_blocks": 2}),
     ("c0", 32, {"col_blocks": 3}), ("c0", 256, {"col_blocks": 4, "seg_len": 16}), ("arxiv", 256, {"col_blocks": 5}),
     ("arxiv", 32, {"col_blocks": 2, "reorder": 0}), ("c0", 64, {"col_blocks": 64}),
-    ("arxiv", 32, {"tune": 1}), ("arxiv", 256, {"tune": 2}), ("c0", 64, {"tune": 2, "seg_len": 32}), ("arxiv", 256, {"tune": 3}),
+    ("arxiv", 32, {"tune": 1}), ("arxiv", 256, {"tune": 1}), ("c0", 64, {"tune": 1, "seg_len": 32}), ("c0", 100, {"tune": 1}),
+    ("arxiv", 256, {"reorder": 0}), ("arxiv", 32, {"reorder": 1}),
 ])
 def test_engine_matches_oracle(shape, K, opts):
     ptr, idx = H.gen_named_graph(shape)
@@ -266,7 +269,11 @@ def test_plan_matches_oracle(shape, seg_len, reorder):
     got = op.plan_arrays()
     assert info["seg_len"] == (seg_len or P.auto_seg_len(len(idx), 32))
     assert info["kslice"] == P.auto_kslice(g.num_v, 32)
-    for k in ("row_perm", "light_desc", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
+    want.update(P.light_stream(want, idx, g.val.cpu().numpy(), 32 // info["lanes"], info["light_steps"]))
+    total = int(want["light_desc"][:, 2].astype(np.int64).sum()) + len(want["light_desc"])
+    assert info["light_steps"] == P.auto_light_steps(32 // info["lanes"], total, info["resident_warps"], len(want["seg_desc"]))
+    assert info["resident_warps"] >= 148 * 8
+    for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
         assert np.array_equal(got[k], want[k]), k
     host = H.plan_host(ptr, 32, seg_len, bool(reorder))
     for k in ("row_perm", "heavy_rows", "heavy_seg0", "seg_desc"):
@@ -293,13 +300,18 @@ def test_column_block_plan_matches_oracle(shape, K, nb, seg_len):
         assert (inf["col_begin"], inf["col_end"]) == (b * cpb, min(M, (b + 1) * cpb))
         assert np.array_equal(got["split"], split)
         want = P.plan(ptr, idx, val, inf["seg_len"], True, rb=split[b], re=split[b + 1], skip_empty=b > 0)
-        for k in ("row_perm", "light_desc", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
+        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"]))
+        for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
             assert np.array_equal(got[k], want[k]), (b, k)
         # every nonzero of the block lies in its band of B rows
         for r0, beg, d, _ in got["light_desc"][:200]:
             assert np.all((idx[beg:beg + d] >= inf["col_begin"]) & (idx[beg:beg + d] < inf["col_end"]))
         for row, beg, d, _ in got["light_desc"]:
             covered[beg:beg + d] += 1
+        # the stream holds every light nonzero exactly once, plus one header per light row
+        lp = got["lpanel"]
+        assert int((lp[:, 0] >= 0).sum()) == int(got["light_desc"][:, 2].sum())
+        assert int(((lp[:, 0] < 0) & (lp[:, 0] != -1)).sum()) == len(got["light_desc"])
         for row, off, ln, nb0 in got["seg_desc"]:
             covered[nb0:nb0 + ln] += 1
     assert np.all(covered == 1)        # the blocks tile A exactly once

@@ -154,3 +154,19 @@ def test_plan_host_matches_oracle():
         assert s[0, 3] == ptr[r] and s[-1, 3] + s[-1, 2] == ptr[r + 1]
         assert np.all(s[1:, 3] == s[:-1, 3] + s[:-1, 2])
         assert s[:, 2].max() - s[:, 2].min() <= 1        # nnz-balanced
+
+
+def test_pack_light_host_matches_oracle():
+    rng = np.random.default_rng(3)
+    for groups, steps in [(1, 256), (4, 64), (8, 32), (2, 7), (32, 32), (1, 1)]:
+        for n in (0, 1, 5, 1000):
+            cost = rng.integers(1, 3 * steps + 2, n).astype(np.int32)
+            dst, ltask, length = H.pack_light_host(cost, groups, steps)
+            odst, otask, olen = P.pack_light(cost, groups, steps)
+            assert np.array_equal(dst, odst) and np.array_equal(ltask, otask) and length == olen, (groups, steps, n)
+            if n:
+                # slots of different rows never collide, tasks tile the panel, offsets stay 16-byte aligned
+                used = np.concatenate([d + np.arange(c) * groups for d, c in zip(dst, cost)])
+                assert len(np.unique(used)) == len(used) and used.max() < length
+                assert np.all(ltask[:, 0] % 2 == 0) and np.all((ltask[:, 1] * groups) % 2 == 0)
+                assert np.array_equal(ltask[1:, 0], (ltask[:, 0] + ltask[:, 1] * groups)[:-1])

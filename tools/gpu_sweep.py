@@ -95,9 +95,8 @@ def bench(name, K, optlist, iters=10):
 
 print(torch.cuda.get_device_name(0), flush=True)
 if mode in ("quick", "full"):
-    parity("c0", 256, tune=5, seg_len=16)
-    parity("arxiv", 256, tune=5, seg_len=8)
-    parity("c0", 128, tune=5, col_blocks=3, seg_len=32)
-    bench("reddit", 256, [{}, {"tune": 5}, {"tune": 5, "block": 64}, {"tune": 5, "block": 256}], iters=5)
-    bench("products", 256, [{"seg_len": 32}, {"seg_len": 32, "tune": 5}], iters=5)
-    bench("arxiv", 256, [{"seg_len": 8}, {"seg_len": 8, "tune": 5}, {"col_blocks": 2}])
+    parity("c0", 32)
+    parity("arxiv", 256)
+    for g, K in (("arxiv", 32), ("arxiv", 256), ("reddit", 32), ("reddit", 256), ("products", 256)):
+        it = 10 if g == "arxiv" else 5
+        bench(g, K, [{}, {"tune": 1}, {"block": 64}, {"block": 256}], iters=it)
