@@ -38,6 +38,7 @@ SIGNATURES = {
     "spmm_b200_create": (_I, [_P, _P, _P, _I, _I, _I, C.POINTER(_P)]),
     "spmm_b200_set_feat": (_I, [_P, _I]),
     "spmm_b200_set_option": (_I, [_P, C.c_char_p, _LL]),
+    "spmm_b200_set_gather": (_I, [_P, _I, C.POINTER(_P), _P, _LL]),
     "spmm_b200_preprocess": (_I, [_P, _P, _P, _P]),
     "spmm_b200_run": (_I, [_P, _P, _P, _P]),
     "spmm_b200_run_profiled": (_I, [_P, _P, _P, _P, C.POINTER(C.c_float)]),

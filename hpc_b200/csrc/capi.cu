@@ -72,7 +72,7 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     if (!strcmp(name, "seg_len") && value >= 0) h->opt_seg_len = value;
     else if (!strcmp(name, "kslice") && value >= 0 && value % 4 == 0) h->opt_kslice = value;
     else if (!strcmp(name, "block") && value >= 32 && value <= 256 && value % 32 == 0) h->opt_block = value;
-    else if (!strcmp(name, "reorder") && (value == 0 || value == 1)) h->opt_reorder = value;
+    else if (!strcmp(name, "reorder") && value >= -1 && value <= 1) h->opt_reorder = value;
     else if (!strcmp(name, "tune") && value >= 0 && value <= 1) h->opt_tune = value;
     else if (!strcmp(name, "light_steps") && value >= 0 && value <= 65536) h->opt_light_steps = value;
     else if (!strcmp(name, "col_blocks") && value >= 0 && value <= 64) h->opt_col_blocks = value;
@@ -85,6 +85,29 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
         return SPMM_B200_EINVAL;
     }
     h->plan.ready = false;
+    return 0;
+}
+
+int spmm_b200_set_gather(spmm_b200_t h, int n_targets, float *const *targets, float *multicast, long long row_offset) {
+    if (!h || n_targets < 0 || n_targets > kMaxGather || (n_targets > 0 && !targets) || row_offset < 0) {
+        set_error("spmm_b200_set_gather: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    if (n_targets > 0 && h->feat % 4 != 0) {
+        set_error("spmm_b200_set_gather: needs feat_in %% 4 == 0");
+        return SPMM_B200_EINVAL;
+    }
+    for (int t = 0; t < n_targets; ++t)
+        if (!targets[t] || ((uintptr_t)targets[t] & 15)) {
+            set_error("spmm_b200_set_gather: target %d is null or not 16-byte aligned", t);
+            return SPMM_B200_EINVAL;
+        }
+    // switching the mode on or off changes which rows the last column block lists
+    if ((n_targets > 0) != (h->n_gather > 0) && h->plan.n_col_blocks > 1) h->plan.ready = false;
+    h->n_gather = n_targets;
+    for (int t = 0; t < kMaxGather; ++t) h->gather[t] = t < n_targets ? targets[t] : nullptr;
+    h->gather_mc = n_targets > 0 ? multicast : nullptr;
+    h->gather_row0 = row_offset;
     return 0;
 }
 

@@ -22,6 +22,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (e__ != cudaSuccess) return ::spmm_b200::cuda_fail(e__, #call, __FILE__, __LINE__); \
     } while (0)
 
+constexpr int kMaxGather = 16;
+
 // One heavy-row segment: `len` nonzeros of `row` starting at CSR position `nnz_begin`,
 // staged at panel[panel_off .. panel_off + roundup2(len)).
 struct SegDesc {
@@ -57,6 +59,11 @@ struct RunArgs {
     int n_seg;
     long long heavy_tasks;     // n_seg * n_slices
     int accumulate;            // 1: continue the chains from vout (column blocks after the first)
+    // stacked-layer epilogue: finished rows also go to every rank's copy of the next layer's B
+    int n_gather;              // 0 = off
+    float *gather[kMaxGather]; // peer-mapped (or local) buffers of b_rows x K floats
+    float *gather_mc;          // NVLS multicast address of the same buffers, or NULL
+    long long gather_row0;     // this handle's first row inside those buffers
 };
 
 // The plan of one column block (the whole matrix when there is a single block).
@@ -99,11 +106,15 @@ struct spmm_b200_handle {
     const int *d_idx = nullptr;
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
-    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = 1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0;
+    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = -1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0;
     int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_elems = 0, stage_in_elems = 0;
+    int n_gather = 0;
+    float *gather[spmm_b200::kMaxGather] = {nullptr};
+    float *gather_mc = nullptr;
+    long long gather_row0 = 0;
     int b_rows = 0;   // rows of B (0 = num_v); > num_v for a row partition of a larger graph
 };
 

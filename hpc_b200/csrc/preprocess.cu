@@ -213,10 +213,17 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
     std::vector<int> row_perm, heavy_rows, heavy_seg0;
     std::vector<SegDesc> segs;
     long long panel_len = 0;
-    // Row order: degree buckets, longest first (shortens the tail, keeps the lanes of a task balanced), or
-    // natural order (option "reorder" = 0; measured within +-3 % on the large shapes, 25-50 % slower on the
-    // one-wave arxiv shape — profiles/r01_sweep.md).
-    const int reorder = (int)h->opt_reorder;
+    // Row order. Degree buckets (longest first) shorten the tail and keep the lanes of a task balanced; natural
+    // order keeps neighbouring rows together, which lets a graph's locality hit in L2. Auto (-1): natural order
+    // when a full warp serves each row (no lanes to balance) and the block is at least 8 waves of tasks long (no
+    // tail to speak of) — measured 12.2 -> 11.3 ms on the products shape, neutral on reddit, and the opposite
+    // (0.14 -> 0.19 ms) on the one-wave arxiv shape, which therefore keeps the buckets (profiles/r01_sweep.md).
+    int reorder = (int)h->opt_reorder;
+    if (reorder < 0) {
+        long long total = 0;
+        for (int r = 0; r < M; ++r) total += re[r] - rb[r] + 1;
+        reorder = (p.lanes == 32 && p.slots > 0 && total >= 8ll * p.slots * 64) ? 0 : 1;
+    }
     bp.reorder = reorder;
     int rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, row_perm, heavy_rows, heavy_seg0,
                             segs, &panel_len);
@@ -355,7 +362,10 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         bp.col_end = nb > 1 ? (b + 1 == nb ? b_rows : (b + 1) * cols_per_block) : b_rows;
         const int *rb = nb > 1 ? split.data() + (size_t)b * M : ptr.data();
         const int *re = nb > 1 ? split.data() + (size_t)(b + 1) * M : ptr.data() + 1;
-        int rc = build_block(h, bp, rb, re, b > 0, stream);
+        // passes after the first skip rows without nonzeros in their band — except the last pass in
+        // stacked-layer mode, which must touch (and forward) every row
+        const bool skip_empty = b > 0 && !(h->n_gather > 0 && b + 1 == nb);
+        int rc = build_block(h, bp, rb, re, skip_empty, stream);
         if (rc) return rc;
     }
     p.ready = true;

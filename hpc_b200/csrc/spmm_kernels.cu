@@ -50,6 +50,21 @@ __device__ __forceinline__ float4 ld_b_row(const float *p) {
 __device__ __forceinline__ void st_c_row(float *p, const float4 &v) {
     __stcs(reinterpret_cast<float4 *>(p), v);
 }
+// A finished C row piece: to vout, and in stacked-layer mode to every rank's copy of the next layer's B —
+// one multimem.st through the NVLS multicast address when there is one, else one st.global per peer-mapped buffer.
+__device__ __forceinline__ void st_final(const RunArgs &a, int row, int col, const float4 &v) {
+    st_c_row(a.vout + (size_t)row * a.feat + col, v);
+    if (a.n_gather) {
+        const size_t off = (size_t)(a.gather_row0 + row) * a.feat + col;
+        if (a.gather_mc) {
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.gather_mc + off), "f"(v.x),
+                         "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+        } else {
+            for (int t = 0; t < a.n_gather; ++t) *reinterpret_cast<float4 *>(a.gather[t] + off) = v;
+        }
+    }
+}
 __device__ __forceinline__ void fma4(float4 &acc, const float4 &b, float v) {
     acc.x = fmaf(b.x, v, acc.x);
     acc.y = fmaf(b.y, v, acc.y);
@@ -98,16 +113,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 //
 // TUNE selects the gathers kept in flight per lane group and the register cap (option "tune";
 // measurements in profiles/r01_sweep.md):
-//   0: 4/VEC gathers in flight, <= 64 registers (4 CTAs of 256 threads per SM)      [default]
-//   1: 8/VEC gathers in flight, <= 80 registers (3 CTAs/SM)
-// Measured and dropped: 2/VEC at 48 registers (spills); L1::no_allocate or L2::evict_last on B rows;
-// gathering B rows into a shared-memory ring with cp.async or with one 1-D TMA copy per row (both ~35 %
-// slower than register gathers on every shape).
+//   0: 4 gathers in flight per lane group: <= 64 registers when a lane owns one float4 (4 CTAs of 256 threads
+//      per SM), <= 80 when it owns two (K >= 256; 3 CTAs/SM)                                     [default]
+//   1: 2 gathers in flight, <= 64 registers
+// Measured and dropped: 8 in flight at K < 256; 2/VEC at 48 registers (spills); L1::no_allocate or
+// L2::evict_last on B rows; gathering B rows into a shared-memory ring with cp.async or with one 1-D TMA copy
+// per row (both ~35 % slower than register gathers on every shape).
 // FULL: every lane's columns are inside the slice (K a multiple of the slice width): no column predicates.
-template <int TUNE>
+template <int TUNE, int VEC>
 struct Tune {
-    static constexpr int kMinBlocks = TUNE == 1 ? 3 : 4;
-    static constexpr int kUnrollBytes = TUNE == 1 ? 8 : 4;   // float4 per lane in flight
+    static constexpr int kMinBlocks = (TUNE == 0 && VEC == 2) ? 3 : 4;
+    static constexpr int kUnroll = TUNE == 1 ? 2 : 4;   // gathers in flight per lane group
 };
 
 // Light rows as a stream: a warp walks one task of the light panel, staged through shared
@@ -119,7 +135,7 @@ struct Tune {
 template <int LANES, int VEC, int TUNE, bool FULL>
 __device__ __forceinline__ void light_stream(const RunArgs &a, long long gw, int lane, int2 *buf, uint64_t *bars) {
     constexpr int GROUPS = 32 / LANES;
-    constexpr int U = Tune<TUNE>::kUnrollBytes / VEC < 1 ? 1 : Tune<TUNE>::kUnrollBytes / VEC;
+    constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
     const int g = lane / LANES;
     const int slice = (int)(gw / a.n_ltask);
@@ -161,10 +177,9 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, long long gw, int
     int cur_row = -1;
     auto flush_row = [&]() {
         if (cur_row >= 0) {
-            float *crow = a.vout + (size_t)cur_row * K + col0;
 #pragma unroll
             for (int v = 0; v < VEC; ++v)
-                if (colok[v]) st_c_row(crow + v * LANES * 4, acc[v]);
+                if (colok[v]) st_final(a, cur_row, col0 + v * LANES * 4, acc[v]);
         }
     };
 
@@ -233,7 +248,7 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, long long gw, int
 template <int LANES, int VEC, int TUNE, bool FULL>
 __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, int lane, int2 *buf, uint64_t *bars) {
     constexpr int GROUPS = 32 / LANES;
-    constexpr int U = Tune<TUNE>::kUnrollBytes / VEC;
+    constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
     const int g = lane / LANES;
     const int slice = (int)(gw / a.n_seg);
@@ -351,12 +366,12 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, in
             sum.z += x.z;
             sum.w += x.w;
         }
-        st_c_row(crow + col, sum);
+        st_final(a, d.row, col, sum);
     }
 }
 
 template <int LANES, int VEC, int TUNE, bool FULL>
-__global__ void __launch_bounds__(256, Tune<TUNE>::kMinBlocks) spmm_kernel(const RunArgs a) {
+__global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_kernel(const RunArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -563,6 +578,11 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         a.heavy_seg0 = bp.d_heavy_seg0;
         a.heavy_tasks = (long long)bp.n_seg * p.n_slices;
         a.accumulate = blk > 0;
+        const bool last = blk + 1 == p.n_col_blocks;   // only the last pass produces final rows
+        a.n_gather = last ? h->n_gather : 0;
+        for (int t = 0; t < kMaxGather; ++t) a.gather[t] = h->gather[t];
+        a.gather_mc = h->gather_mc;
+        a.gather_row0 = h->gather_row0;
         if (p.scalar) {
             a.light_tasks_per_slice = a.n_light;
             const int warps = p.block / 32;

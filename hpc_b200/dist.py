@@ -104,6 +104,40 @@ class ShardedSpMM:
                 w.wait()
         return full
 
+    # ---- fused epilogue: the kernel itself delivers C rows to every rank (NVLink peer / multicast stores) ----
+
+    def enable_fused_gather(self, n_buffers: int = 2, use_multicast: bool = True):
+        """Allocates `n_buffers` symmetric (peer-mapped) full-size C buffers through torch's symmetric memory
+        (plumbing only) and points the operator's epilogue at them. Call before preprocess. Layers alternate
+        between the buffers so a layer's input is never overwritten by its own output."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group or dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._sym_bufs, self._sym_hdls = [], []
+        for _ in range(n_buffers):
+            t = symm_mem.empty(self.num_v * self.feat, dtype=torch.float32, device=dev)
+            self._sym_bufs.append(t)
+            self._sym_hdls.append(symm_mem.rendezvous(t, group))
+        self._use_mc = bool(use_multicast and getattr(self._sym_hdls[0], "has_multicast_support", lambda *a: False) is not None
+                            and self._sym_hdls[0].multicast_ptr)
+        self._select_gather(0)
+        return self._sym_bufs
+
+    def _select_gather(self, i: int):
+        h = self._sym_hdls[i]
+        mc = h.multicast_ptr if self._use_mc else 0
+        self.op.set_gather([int(p) for p in h.buffer_ptrs], self.row_begin, multicast=mc)
+        self._sym_cur = i
+
+    def run_fused(self, vin, vout_local, buffer: int = 0) -> torch.Tensor:
+        """SpMM whose epilogue also writes this rank's rows into every rank's symmetric buffer `buffer`; after
+        the cross-rank barrier the returned tensor holds the full C on every rank. No collective call."""
+        if self._sym_cur != buffer:
+            self._select_gather(buffer)
+        self.op.run(vin, vout_local)
+        self._sym_hdls[buffer].barrier()
+        return self._sym_bufs[buffer]
+
     def close(self):
         if hasattr(self.op, "close"):
             self.op.close()

@@ -92,6 +92,13 @@ class SpMMB200(SpMM):
             if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
                 raise ValueError(f"{name}: need a contiguous CUDA float32 tensor of >= {n} elements")
 
+    def set_gather(self, targets, row_offset: int, multicast: int = 0) -> None:
+        """Stacked-layer epilogue: finished C rows also go to `targets` (device pointers as ints, or CUDA
+        tensors) at row `row_offset`, or once through the NVLS `multicast` address. [] switches it off."""
+        ptrs = [t.data_ptr() if hasattr(t, "data_ptr") else int(t) for t in targets]
+        arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
+        check(lib.spmm_b200_set_gather(self._h, len(ptrs), arr, C.c_void_p(multicast or 0), int(row_offset)))
+
     def preprocess(self, vin, vout) -> None:
         self._check_io(vin, vout)
         check(lib.spmm_b200_preprocess(self._h, _ptr(vin), _ptr(vout), _stream()))

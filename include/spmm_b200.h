@@ -43,7 +43,8 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "seg_len"   nonzeros per heavy-row segment; rows longer than this are split (0 = auto)
  *   "kslice"    feature columns per pass over the graph (0 = auto; else multiple of 4)
  *   "block"     threads per CTA (multiple of 32)
- *   "reorder"   1 = degree-bucketed row order (default), 0 = natural order
+ *   "reorder"   1 = degree-bucketed row order, 0 = natural order, -1 (default) = natural when a full warp
+ *               serves each row (K >= 128) and the graph is at least 8 waves of tasks long, else bucketed
  *   "light_steps" entries per lane group and stream task (0 = auto: 64 / groups, at least 16;
  *               128 on very large graphs at K >= 128; smaller on graphs of fewer than 4 waves of tasks, to
  *               fill whole waves of resident warps)
@@ -72,6 +73,15 @@ int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream);
 /* run, plus the device time of its kernel in milliseconds (CUDA events on `stream` around the
  * launch). Synchronises. Counterpart of getCUDATime (PA4/handout/include/util.h:131-139). */
 int spmm_b200_run_profiled(spmm_b200_t h, const float *vin, float *vout, void *stream, float *ms);
+
+/* Stacked-layer epilogue (no reference counterpart). Besides vout, every finished C row r is
+ * also stored at targets[t] + (row_offset + r) * feat_in for each t < n_targets — e.g. every rank's copy of the next
+ * layer's B, mapped through NVLink peer memory — or, when `multicast` is non-NULL, once through that NVLS multicast
+ * address of the same buffers (multimem.st). The all-gather of C then needs no separate collective: after the
+ * kernel and a cross-rank barrier every rank holds the full C. Targets are device pointers, 16-byte aligned, of
+ * b_rows * feat_in floats; n_targets <= 16; 0 switches the mode off. Set it before preprocess when column blocks
+ * are in use (changing it invalidates such a plan). */
+int spmm_b200_set_gather(spmm_b200_t h, int n_targets, float *const *targets, float *multicast, long long row_offset);
 
 /* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). */
 int spmm_b200_destroy(spmm_b200_t h);

@@ -151,6 +151,11 @@ def auto_light_steps(groups: int, total_cost: int, slots: int, heavy_tasks: int)
     return min(max(st, 16), dflt)
 
 
+def auto_reorder(lanes: int, total_cost: int, slots: int) -> bool:
+    """Natural order (False) when a full warp serves each row and the block is >= 8 waves of 64-entry tasks."""
+    return not (lanes == 32 and slots > 0 and total_cost >= 8 * slots * 64)
+
+
 def pack_light(cost, groups: int, steps: int):
     """Light-stream packing. cost[i] = nonzeros + 1 of the i-th light row in plan order. A row goes to the
     least-filled lane of the current task (lowest index on ties); when that lane is non-empty and would exceed

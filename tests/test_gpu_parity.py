@@ -329,6 +329,20 @@ def test_unsorted_columns_fall_back_to_one_block():
     op.close()
 
 
+def test_auto_row_order_rule():
+    """Small graphs keep degree buckets; many-wave graphs at K >= 128 use natural order (plan_info reports it)."""
+    ptr, idx = H.gen_named_graph("arxiv")
+    g, vin, vout = dev_inputs(ptr, idx, 256)
+    op = H.SpMMB200(g, 256)
+    op.preprocess(vin, vout)
+    info = op.plan_info()
+    total = int(np.diff(ptr).astype(np.int64).sum()) + g.num_v
+    assert info["reorder"] == int(P.auto_reorder(info["lanes"], total, info["resident_warps"])) == 1
+    assert P.auto_reorder(32, 126_000_000, info["resident_warps"]) is False
+    assert P.auto_reorder(8, 126_000_000, info["resident_warps"]) is True
+    op.close()
+
+
 def test_auto_col_blocks_rule():
     assert P.auto_col_blocks(232965, 256, 114615892, 232965) == 5       # reddit K=256: B = 239 MB
     assert P.auto_col_blocks(232965, 32, 114615892, 232965) == 1        # B = 30 MB fits
@@ -454,3 +468,48 @@ def test_cpp_harness_validation_and_timing(tmp_path):
     r = subprocess.run([exe, "--dataset", "c0", "--datadir", str(tmp_path), "--len", "256"], capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "[  PASSED  ] 2 tests." in r.stdout, r.stdout + r.stderr
+
+
+def test_run_all_sweep_subset(tmp_path):
+    """run_all.sh restated: a subset of the 13 dataset shapes through the harness, log parsable like plot.py does."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    log = str(tmp_path / "out.log")
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "run_all.py"), "--len", "32", "--log", log, "collab", "ddi", "am"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    text = open(log).read()
+    # plot.py:13-27: dataset from `dset = "name"`, times from `time = x (double)`
+    assert re.findall(r'dset = "([a-z_.]+)"', text) == ["collab", "ddi", "am"]
+    assert len(re.findall(r"time = ([0-9.e+-]+) \(double\)", text)) == 3
+    assert text.count("[  PASSED  ] 2 tests.") == 3
+
+
+@pytest.mark.parametrize("shape,K,opts", [("c0", 32, {}), ("arxiv", 256, {}), ("c0", 256, {"col_blocks": 3, "seg_len": 32})])
+def test_stacked_layer_epilogue_local_targets(shape, K, opts):
+    """spmm_b200_set_gather with local buffers standing in for peers: every finished row lands at its offset in
+    every target, bit-equal to vout; rows outside this handle's block stay untouched."""
+    ptr, idx = H.gen_named_graph(shape)
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    M = g.num_v
+    pad = 5
+    targets = [torch.full(((M + 2 * pad) * K,), -7.0, device=DEV) for _ in range(3)]
+    op = H.SpMMB200(g, K, **opts)
+    op.set_gather(targets, row_offset=pad)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    torch.cuda.synchronize()
+    for t in targets:
+        assert torch.equal(t[pad * K:(pad + M) * K], vout[: M * K])
+        assert bool((t[: pad * K] == -7.0).all()) and bool((t[(pad + M) * K:] == -7.0).all())
+    check_against_oracle(ptr, idx, K, op, g, vin, vout[: M * K].cpu().numpy().reshape(M, K))
+    # off again: targets no longer written
+    op.set_gather([], 0)
+    op.preprocess(vin, vout)
+    for t in targets:
+        t.fill_(1.0)
+    op.run(vin, vout)
+    torch.cuda.synchronize()
+    assert all(bool((t == 1.0).all()) for t in targets)
+    op.close()
