@@ -138,6 +138,7 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, long long gw, int
     constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
     const int g = lane / LANES;
+    if (a.n_ltask == 0) return;   // every row is heavy: the spare warps of the last CTA have nothing to do
     const int slice = (int)(gw / a.n_ltask);
     if (slice >= a.n_slices) return;
     const int task = (int)(gw - (long long)slice * a.n_ltask);

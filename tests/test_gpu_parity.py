@@ -187,6 +187,35 @@ def test_single_long_row(length, K):
     op.close()
 
 
+@pytest.mark.parametrize("K", [32, 256, 100])
+def test_every_row_heavy(K):
+    """No light rows at all (the ddi shape at K=32 is like this): the stream part of the launch is empty."""
+    m, d = 37, 300
+    rng = np.random.default_rng(7)
+    ptr = (np.arange(m + 1) * d).astype(np.int32)
+    idx = np.concatenate([np.sort(rng.choice(4096, d, replace=False)) for _ in range(m)]).astype(np.int32)
+    ptr_full = np.concatenate([ptr, np.full(4096 - m, ptr[-1], np.int32)])       # square: 4096 rows, the rest empty
+    for rows_ptr in (ptr_full,):
+        op, g, vin, vout, got = run_engine(rows_ptr, idx, K, seg_len=16)
+        assert op.plan_info()["n_heavy"] == m
+        check_against_oracle(rows_ptr, idx, K, op, g, vin, got)
+        op.close()
+    # and with literally zero light rows (rectangular block: 37 rows of a 4096-column matrix)
+    g, vin, vout = dev_inputs(ptr, idx, K, b_rows=4096)
+    op = H.SpMMB200(g, K, b_rows=4096, seg_len=16)
+    op.preprocess(vin, vout)
+    info = op.plan_info()
+    assert info["n_light"] == 0 and info["n_ltask"] == 0 and info["n_heavy"] == m
+    op.run(vin, vout)
+    torch.cuda.synchronize()
+    got = vout[: m * K].cpu().numpy().reshape(m, K)
+    val, b = g.val.cpu().numpy(), vin.cpu().numpy().reshape(4096, K)
+    want = np.stack([(b[idx[ptr[r]:ptr[r + 1]]].astype(np.float64) * val[ptr[r]:ptr[r + 1], None]).sum(0) for r in range(m)])
+    scale = np.stack([np.abs(b[idx[ptr[r]:ptr[r + 1]]].astype(np.float64) * val[ptr[r]:ptr[r + 1], None]).sum(0) for r in range(m)])
+    assert np.all(np.abs(got - want) <= TOL * scale)
+    op.close()
+
+
 def test_nnz_zero_and_empty_graph():
     ptr = np.zeros(6, np.int32)
     idx = np.zeros(0, np.int32)
@@ -476,12 +505,12 @@ def test_run_all_sweep_subset(tmp_path):
     import subprocess
     from conftest import ROOT
     log = str(tmp_path / "out.log")
-    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "run_all.py"), "--len", "32", "--log", log, "collab", "ddi", "am"],
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "run_all.py"), "--len", "32", "--log", log, "collab", "ddi", "am"],   # ddi at K=32: every row is heavy
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     text = open(log).read()
     # plot.py:13-27: dataset from `dset = "name"`, times from `time = x (double)`
-    assert re.findall(r'dset = "([a-z_.]+)"', text) == ["collab", "ddi", "am"]
+    assert re.findall(r'dset = "([a-z_.0-9]+)"', text) == ["collab", "ddi", "am"]
     assert len(re.findall(r"time = ([0-9.e+-]+) \(double\)", text)) == 3
     assert text.count("[  PASSED  ] 2 tests.") == 3
 
