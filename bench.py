@@ -176,6 +176,39 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def quick_measure(H, torch, shape, k, dev, steps=10, warmup=3):
+    """Kernel-only numbers for one more BASELINE config on the same GPU (L2 flushed between iterations)."""
+    ptr, idx = H.gen_named_graph(shape, SEED)
+    m, nnz = len(ptr) - 1, len(idx)
+    g = H.CSR(m, nnz, torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev),
+              H.fill_normal(torch.empty(nnz, dtype=torch.float32, device=dev), SEED, 1))
+    vin = H.fill_normal(torch.empty(m * k, dtype=torch.float32, device=dev), SEED, 2)
+    vout = torch.empty(m * k, dtype=torch.float32, device=dev)
+    op = H.SpMMB200(g, k)
+    op.preprocess(vin, vout)
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        flush.zero_()
+        op.run(vin, vout)
+    ts = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        op.run(vin, vout)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    op.close()
+    ms = float(np.mean(ts))
+    peak, _ = measured_peaks()
+    bm = bytes_min(m, nnz, k)
+    return {"workload": f"{shape}_k{k}", "num_v": m, "nnz": nnz, "K": k, "ms_per_step": round(ms, 5),
+            "gflops": round(2.0 * nnz * k / ms / 1e6, 1), "hbm_gbs_bytes_min": round(bm / ms / 1e6, 1),
+            "roofline_frac": round(bm / ms / 1e6 / peak, 4), "gather_gbs": round(bytes_gather(m, nnz, k) / ms / 1e6, 1),
+            "l2": "flushed between iterations"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -327,6 +360,10 @@ def run_b200(args):
             "clocks": clocks.summary(),
             "wall_s_timed_region": round(wall, 4),
         }
+        if world == 1 and not args.no_also:
+            # the other single-GPU BASELINE configs, kernel-only, so that one line covers K=32 and K=256
+            line["also"] = [quick_measure(H, torch, sh, kk, dev) for sh, kk in (("arxiv", 32), ("arxiv", 256))
+                            if f"{sh}_k{kk}" != args.workload]
         if world == 1 and not args.no_cpu_baseline:
             gf, desc, cores, _, _ = cpu_sample(ptr, idx, k, args.cpu_seconds)
             line["cpu_baseline"] = {"value": round(gf, 3), "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc}
@@ -355,6 +392,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="reddit_k256", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the kernel-only numbers of the other configs")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (tuning runs only)")
     args = ap.parse_args()

@@ -187,8 +187,32 @@ int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *s
         h->stage_elems = n;
         h->stage_in_elems = nb;
     }
-    SB_CUDA(cudaMemcpyAsync(h->d_stage_in, h_vin, nb * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = launch_spmm(h, h->d_stage_in, h->d_stage_out, s, &h->plan.launches);
+    int rc;
+    const Plan &p = h->plan;
+    if (p.n_col_blocks > 1) {
+        // Column block b only gathers from its band of B rows: upload the bands in order on a second stream and
+        // let each pass wait for its own band, so the PCIe transfer of later bands overlaps the earlier passes.
+        if (!h->copy_stream) SB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        while ((int)h->band_events.size() < p.n_col_blocks) {
+            cudaEvent_t e;
+            SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->band_events.push_back(e);
+        }
+        // the copy stream must not run ahead of work already queued on the caller's stream
+        SB_CUDA(cudaEventRecord(h->band_events[0], s));
+        SB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->band_events[0], 0));
+        for (int b = 0; b < p.n_col_blocks; ++b) {
+            const size_t off = (size_t)p.blocks[b].col_begin * h->feat;
+            const size_t cnt = (size_t)(p.blocks[b].col_end - p.blocks[b].col_begin) * h->feat;
+            SB_CUDA(cudaMemcpyAsync(h->d_stage_in + off, h_vin + off, cnt * sizeof(float), cudaMemcpyHostToDevice,
+                                    h->copy_stream));
+            SB_CUDA(cudaEventRecord(h->band_events[b], h->copy_stream));
+        }
+        rc = launch_spmm(h, h->d_stage_in, h->d_stage_out, s, &h->plan.launches, h->band_events.data());
+    } else {
+        SB_CUDA(cudaMemcpyAsync(h->d_stage_in, h_vin, nb * sizeof(float), cudaMemcpyHostToDevice, s));
+        rc = launch_spmm(h, h->d_stage_in, h->d_stage_out, s, &h->plan.launches);
+    }
     if (rc) return rc;
     SB_CUDA(cudaMemcpyAsync(h_vout, h->d_stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
@@ -200,6 +224,8 @@ int spmm_b200_destroy(spmm_b200_t h) {
     free_plan(h->plan);
     cudaFree(h->d_stage_in);
     cudaFree(h->d_stage_out);
+    for (cudaEvent_t e : h->band_events) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return 0;
 }

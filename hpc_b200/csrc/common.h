@@ -111,6 +111,8 @@ struct spmm_b200_handle {
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_elems = 0, stage_in_elems = 0;
+    cudaStream_t copy_stream = nullptr;          // run_host: H2D of B bands
+    std::vector<cudaEvent_t> band_events;
     int n_gather = 0;
     float *gather[spmm_b200::kMaxGather] = {nullptr};
     float *gather_mc = nullptr;
@@ -125,8 +127,10 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream);
 void free_plan(Plan &p);
 
 // spmm_kernels.cu
+// band_ready: NULL, or one event per column block that the stream waits on before that block's pass
+// (run_host uploads B band by band on a second stream while earlier passes compute)
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
-                int *launches);
+                int *launches, const cudaEvent_t *band_ready = nullptr);
 int resident_warps(int lanes, int vec, int tune, int block);
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
                       int *d_split, int *d_unsorted, cudaStream_t stream);

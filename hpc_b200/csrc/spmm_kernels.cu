@@ -550,12 +550,13 @@ int slots_shape(int block, int tune) {
 }  // namespace
 
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
-                int *launches) {
+                int *launches, const cudaEvent_t *band_ready) {
     const Plan &p = h->plan;
     *launches = 0;
     if (h->num_v == 0 || h->feat == 0) return 0;
     for (int blk = 0; blk < p.n_col_blocks; ++blk) {
         const BlockPlan &bp = p.blocks[blk];
+        if (band_ready) SB_CUDA(cudaStreamWaitEvent(stream, band_ready[blk], 0));
         if (blk > 0 && bp.n_light == 0 && bp.n_seg == 0) continue;
         RunArgs a;
         a.idx = h->d_idx;
