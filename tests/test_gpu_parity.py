@@ -546,3 +546,27 @@ def test_stacked_layer_epilogue_local_targets(shape, K, opts):
     torch.cuda.synchronize()
     assert all(bool((t == 1.0).all()) for t in targets)
     op.close()
+
+
+# ---- the reference's own, unmodified test driver with the engine dropped in ----------
+
+_DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "unit_tests_dropin")
+
+
+@pytest.mark.skipif(not os.path.exists(_DROPIN), reason="oracle/_ref/unit_tests_dropin not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("shape,K", [("c0", 32), ("arxiv", 32), ("arxiv", 256), ("ddi", 256)])
+def test_reference_test_driver_with_engine_dropped_in(tmp_path, shape, K):
+    """PA4/handout/test/main.cpp + test_spmm.cu, compiled unmodified with tests/cpp/dropin/spmm_opt.h in place of the
+    handout's: SpMMTest.validation compares the engine with the reference's SpMMRef kernel on cuRAND inputs and applies
+    the reference's valid(); cusparse_performance / opt_performance time cuSPARSE and the engine the reference's way."""
+    import re
+    import subprocess
+    ptr, idx = H.gen_named_graph(shape)
+    H.write_graph(str(tmp_path), shape, ptr, idx, text=False)     # the reference's binary dump format
+    r = subprocess.run([_DROPIN, "--dataset", shape, "--datadir", str(tmp_path), "--len", str(K)], capture_output=True,
+                       text=True, timeout=600)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "[       OK ] SpMMTest.validation" in out and "[  PASSED  ] 3 tests." in out, out[-3000:]
+    times = [float(x) for x in re.findall(r"time = ([0-9.e+-]+) \(double\)", out)]
+    assert len(times) == 2 and all(t > 0 for t in times)          # cuSPARSE, then the engine (test_spmm.cu:46-62)
