@@ -360,6 +360,7 @@ def run_b200(args):
                 "peak_source": peak_src, "kernel_ms": round(kernel_ms / n_launch, 5),
                 "algorithmic_bytes": int(total_bytes // n_launch),
                 "gather_gbs": round(bytes_gather(lm, lnnz, k) / kernel_ms / 1e6, 1),
+                "binding": binding_bound(args.workload, bytes_gather(lm, lnnz, k) / kernel_ms / 1e6, kernel_ms / n_launch, peak, world),
                 "note": "per launch = per column-block pass (equal shares of the step); rank 0's partition; algorithmic bytes = "
                         "ptr+col+val+B once+C once (SURVEY.md 8d). The binding bound is the L2->SM gather of B rows (or HBM when B "
                         "is far larger than L2), not compulsory bytes: see DESIGN.md section 3 and profiles/r01_sweep.md",
@@ -394,6 +395,26 @@ NCU_TRAFFIC = {
     "arxiv_k32": int(33.74e6 + 0.18e6),           # prof_arxiv_k32_r01d
     "arxiv_k256": int(599.96e6 + 119.85e6),       # prof_arxiv_k256_r01d
 }
+
+
+# What actually binds each workload (ncu, profiles/r01_ncu_summary.md). "l2_fabric": bytes gathered L2 -> SM per second
+# against the fabric rate at which ncu shows lts2xbar 100 % busy (19.58 TB/s at 84.6 % => 23.1 TB/s). "hbm_traffic": the
+# DRAM bytes ncu measured per launch, moved in the live kernel time, against the measured HBM peak.
+BINDING = {"reddit_k256": "l2_fabric", "reddit_k32": "l2_fabric", "products_k256": "hbm_traffic",
+           "arxiv_k256": "hbm_traffic", "arxiv_k32": "latency", "c0_k32": "latency"}
+L2_FABRIC_PEAK_GBS = 23100.0
+
+
+def binding_bound(workload, gather_gbs, kernel_ms_per_launch, peak_hbm, world):
+    kind = BINDING.get(workload, "latency")
+    if kind == "l2_fabric":
+        return {"bound": "l2_fabric", "achieved": round(gather_gbs, 1), "peak": L2_FABRIC_PEAK_GBS, "unit": "GB/s",
+                "frac": round(gather_gbs / L2_FABRIC_PEAK_GBS, 4), "source": "ncu lts2xbar_cycles_active (profiles/r01_ncu_summary.md)"}
+    if kind == "hbm_traffic" and world == 1 and workload in NCU_TRAFFIC:
+        a = NCU_TRAFFIC[workload] / kernel_ms_per_launch / 1e6
+        return {"bound": "hbm_traffic", "achieved": round(a, 1), "peak": peak_hbm, "unit": "GB/s", "frac": round(a / peak_hbm, 4),
+                "source": "ncu dram bytes per launch / live kernel time"}
+    return {"bound": kind}
 
 
 def main():

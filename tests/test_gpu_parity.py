@@ -570,3 +570,65 @@ def test_reference_test_driver_with_engine_dropped_in(tmp_path, shape, K):
     assert "[       OK ] SpMMTest.validation" in out and "[  PASSED  ] 3 tests." in out, out[-3000:]
     times = [float(x) for x in re.findall(r"time = ([0-9.e+-]+) \(double\)", out)]
     assert len(times) == 2 and all(t > 0 for t in times)          # cuSPARSE, then the engine (test_spmm.cu:46-62)
+
+
+def test_run_is_capturable_in_a_cuda_graph():
+    """run() makes no host synchronisation, so a launch-bound caller can capture it once and replay it."""
+    ptr, idx = H.gen_named_graph("arxiv")
+    K = 32
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    op = H.SpMMB200(g, K)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    torch.cuda.synchronize()
+    want = vout.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        op.run(vin, vout)                      # warm-up on the capture stream
+        s.synchronize()
+        with torch.cuda.graph(graph, stream=s):
+            op.run(vin, vout)
+    for _ in range(3):
+        vout.fill_(float("nan"))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(vout, want)
+    op.close()
+
+
+def test_fuzz_random_graphs_and_options():
+    """Seeded sweep over small random graphs x K x plan options: every combination must satisfy the parity bar."""
+    rng = np.random.default_rng(2024)
+    for case in range(48):
+        m = int(rng.integers(1, 1500))
+        mean = float(rng.choice([0.5, 3, 20, 120]))
+        deg = np.minimum(rng.poisson(mean, m) * (rng.random(m) < 0.8) + (rng.random(m) < 0.02) * rng.integers(0, m + 1, m), m).astype(np.int64)
+        ptr = np.zeros(m + 1, np.int32)
+        np.cumsum(deg, out=ptr[1:])
+        idx = np.concatenate([np.sort(rng.choice(m, int(d), replace=False)) for d in deg] + [np.zeros(0, np.int64)]).astype(np.int32)
+        K = int(rng.choice([4, 8, 12, 32, 36, 64, 128, 256, 260, 512, 5, 33]))
+        opts = {}
+        if K % 4 == 0:
+            if rng.random() < 0.6:
+                opts["seg_len"] = int(rng.choice([1, 2, 7, 16, 64, 300]))
+            if rng.random() < 0.4:
+                opts["col_blocks"] = int(rng.integers(1, 7))
+            if rng.random() < 0.4:
+                opts["light_steps"] = int(rng.choice([1, 2, 5, 16, 100]))
+            if rng.random() < 0.3:
+                opts["kslice"] = int(rng.choice([4, 16, 32, 64, 128]))
+            if rng.random() < 0.3:
+                opts["tune"] = 1
+            if rng.random() < 0.3:
+                opts["block"] = int(rng.choice([32, 64, 256]))
+        if rng.random() < 0.4:
+            opts["reorder"] = int(rng.integers(0, 2))
+        op, g, vin, vout, got = run_engine(ptr, idx, K, **opts)
+        try:
+            check_against_oracle(ptr, idx, K, op, g, vin, got)
+        except AssertionError as e:
+            raise AssertionError(f"fuzz case {case}: m={m} nnz={len(idx)} K={K} opts={opts}: {e}")
+        finally:
+            op.close()

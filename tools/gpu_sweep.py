@@ -95,10 +95,7 @@ def bench(name, K, optlist, iters=10):
 
 print(torch.cuda.get_device_name(0), flush=True)
 if mode in ("quick", "full"):
-    parity("c0", 32)
-    parity("arxiv", 256)
-    parity("c0", 256, tune=1, col_blocks=2)
-    for g, K in (("reddit", 256), ("products", 256)):
-        bench(g, K, [{"reorder": r, "light_steps": st} for r in (0, 1) for st in (64, 128, 256)] + [{"tune": 1}], iters=5)
-    for g, K in (("arxiv", 32), ("arxiv", 256), ("reddit", 32)):
-        bench(g, K, [{}, {"tune": 1}], iters=10 if g == "arxiv" else 5)
+    parity("arxiv", 256, kslice=128)
+    bench("arxiv", 256, [{}, {"kslice": 128}, {"kslice": 64}, {"kslice": 128, "tune": 1}], iters=10)
+    bench("collab", 256, [{}, {"kslice": 128}], iters=10)
+    bench("youtube", 256, [{}, {"kslice": 128}], iters=10)
