@@ -67,7 +67,8 @@ int spmm_b200_preprocess(spmm_b200_t h, const float *vin, float *vout, void *str
 
 /* SpMM::run(float *vin, float *vout)  (spmm_base.h:32; PA4/handout/src/spmm_ref.cu:27-30).
  * Asynchronous on `stream` (a cudaStream_t; NULL = the default stream, as in the reference).
- * Fully overwrites vout[num_v*feat_in]; does not depend on its previous contents. */
+ * Fully overwrites vout[num_v*feat_in]; does not depend on its previous contents. Runs of one handle must not
+ * overlap in time (they share the handle's partial-row workspace): issue them on one stream, or synchronise. */
 int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream);
 
 /* run, plus the device time of its kernel in milliseconds (CUDA events on `stream` around the

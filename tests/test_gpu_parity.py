@@ -404,12 +404,12 @@ def test_fill_and_valid_match_oracle():
         assert abs(refshim.ref_valid(dy, dy2, y.size) - want) <= 3
 
 
-def test_row_partitions_reproduce_full_result():
+@pytest.mark.parametrize("shape,K,extra", [("arxiv", 32, {}), ("c0", 64, {"col_blocks": 3}), ("c0", 256, {"col_blocks": 2, "reorder": 0})])
+def test_row_partitions_reproduce_full_result(shape, K, extra):
     """row blocks balanced by nnz, B replicated; concatenated block results equal the
-    single-GPU result bit for bit (per-row arithmetic depends only on the row and seg_len)."""
-    ptr, idx = H.gen_named_graph("arxiv")
-    K = 32
-    opf, g, vin, vout, full = run_engine(ptr, idx, K, seg_len=256)
+    single-GPU result bit for bit (per-row arithmetic depends only on the row, seg_len and the column bands)."""
+    ptr, idx = H.gen_named_graph(shape)
+    opf, g, vin, vout, full = run_engine(ptr, idx, K, seg_len=256, **extra)
     M = g.num_v
     val = g.val
     for parts in (2, 8):
@@ -422,8 +422,9 @@ def test_row_partitions_reproduce_full_result():
             e0, e1 = int(ptr[r0]), int(ptr[r1])
             gl = H.CSR(r1 - r0, e1 - e0, torch.from_numpy(lptr).to(DEV), g.idx[e0:e1].clone(), val[e0:e1].clone())
             o = torch.full((max(1, (r1 - r0) * K),), float("nan"), device=DEV)
-            op = H.SpMMB200(gl, K, b_rows=M, seg_len=256)
+            op = H.SpMMB200(gl, K, b_rows=M, seg_len=256, **extra)
             op.preprocess(vin, o)
+            assert op.plan_info()["n_col_blocks"] == extra.get("col_blocks", 1)
             op.run(vin, o)
             outs.append(o[: (r1 - r0) * K].cpu().numpy())
             op.close()
