@@ -66,6 +66,8 @@ def check_against_oracle(ptr, idx, K, op, g, vin, got):
     assert np.array_equal(got[light].view(np.int32), ref[light].view(np.int32)), "whole rows must be bit-exact"
     ab = O.spmm_abssum(ptr, idx, val, b, K)
     assert np.all(np.abs(got.astype(np.float64) - ref) <= TOL * ab + 1e-30)
+    # regression guard, well inside the stated tolerance: re-associated fp32 sums stay within a few ulp of the terms
+    assert np.all(np.abs(got.astype(np.float64) - ref) <= 2e-6 * ab + 1e-30)
     # the reference's pass criterion, candidate first (test_spmm.cu:43)
     assert O.validate_float(got, ref) < M * K // 10000 + 1
     return ref
@@ -108,6 +110,29 @@ def test_engine_vs_reference_kernel(shape, K):
     # and the oracle agrees with the reference kernel bit for bit at this size too
     ora = check_against_oracle(ptr, idx, K, op, g, vin, got)
     assert np.array_equal(ora.view(np.int32), ref.view(np.int32))
+    op.close()
+
+
+@pytest.mark.skipif(not refshim.available(), reason="oracle/_ref not built")
+def test_subnormal_inputs_flush_like_the_reference():
+    """The handout is built with --use_fast_math, so spmm_kernel_ref is an FFMA.FTZ chain: subnormal operands and
+    results are flushed to zero. The engine is built with -ftz=true and must agree bit for bit on such inputs."""
+    ptr, idx = H.gen_named_graph("c0")
+    K = 32
+    M, nnz = len(ptr) - 1, len(idx)
+    rng = np.random.default_rng(11)
+    val = rng.normal(0, 0.1, nnz).astype(np.float32)
+    b = rng.normal(0, 0.1, (M, K)).astype(np.float32)
+    b[rng.random((M, K)) < 0.3] = np.float32(1e-40)                 # subnormal operands
+    b[rng.random((M, K)) < 0.2] *= np.float32(1e-37)                # products that underflow
+    val[rng.random(nnz) < 0.2] = np.float32(3e-39)
+    op, g, vin, vout, got = run_engine(ptr, idx, K, val=val, b=b, seg_len=1 << 20)     # every row whole
+    ref_out = torch.zeros(M * K, device=DEV)
+    refshim.ref_spmm(g.ptr, g.idx, g.val, vin, ref_out, M, nnz, K)
+    ref = ref_out.cpu().numpy().reshape(M, K)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+    assert np.array_equal(O.spmm_f32(ptr, idx, val, b, K, ftz=True).view(np.int32), ref.view(np.int32))
+    assert not np.array_equal(O.spmm_f32(ptr, idx, val, b, K, ftz=False).view(np.int32), ref.view(np.int32))   # the inputs do exercise FTZ
     op.close()
 
 
