@@ -357,6 +357,7 @@ def run_b200(args):
                 "achieved": round(total_bytes / kernel_ms / 1e6, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(total_bytes / kernel_ms / 1e6 / peak, 4),
                 "traffic": NCU_TRAFFIC.get(args.workload) if world == 1 else None,
+                "l2_hit_pct_ncu": NCU_L2_HIT_PCT.get(args.workload) if world == 1 else None,
                 "peak_source": peak_src, "kernel_ms": round(kernel_ms / n_launch, 5),
                 "algorithmic_bytes": int(total_bytes // n_launch),
                 "gather_gbs": round(bytes_gather(lm, lnnz, k) / kernel_ms / 1e6, 1),
@@ -396,6 +397,9 @@ NCU_TRAFFIC = {
     "arxiv_k256": int(599.96e6 + 119.85e6),       # prof_arxiv_k256_r01d
 }
 
+
+# lts__t_sector_hit_rate.pct of the same captures: the L2 hit rate, essentially that of the B-row gathers
+NCU_L2_HIT_PCT = {"reddit_k256": 94.9, "products_k256": 33.2, "arxiv_k32": 55.2, "arxiv_k256": 32.0}
 
 # What actually binds each workload (ncu, profiles/r01_ncu_summary.md). "l2_fabric": bytes gathered L2 -> SM per second
 # against the fabric rate at which ncu shows lts2xbar 100 % busy (19.58 TB/s at 84.6 % => 23.1 TB/s). "hbm_traffic": the
