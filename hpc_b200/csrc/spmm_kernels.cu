@@ -349,13 +349,13 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, in
     if (lane == 0) {
         int *cnt = a.seg_count + (size_t)hrow * a.n_slices + slice;
         last = atomicAdd(cnt, 1) == s1 - s0 - 1;
-        if (last) {
-            *cnt = 0;
-            __threadfence();
-        }
+        if (last) *cnt = 0;
     }
     last = __shfl_sync(kFull, last, 0);
     if (!last) return;
+    // acquire side, executed by every lane that is about to read the other warps' partials (the writers fenced
+    // after their stores and before the counter was bumped)
+    __threadfence();
     float *crow = a.vout + (size_t)d.row * K;
     for (int col = slice * a.kslice + lane * 4; col < col_end; col += 128) {
         const float *p = a.part + (size_t)s0 * K + col;
