@@ -132,6 +132,7 @@ void free_plan(Plan &p);
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
                 int *launches, const cudaEvent_t *band_ready = nullptr);
 int resident_warps(int lanes, int vec, int tune, int block);
+int launch_check_cols(const int *d_idx, long long nnz, int b_rows, int *d_bad, cudaStream_t stream);
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
                       int *d_split, int *d_unsorted, cudaStream_t stream);
 int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, const int *d_idx, const float *d_val,

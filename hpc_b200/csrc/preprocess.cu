@@ -328,6 +328,22 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         return SPMM_B200_EINVAL;
     }
 
+    {   // columns must address rows of B
+        int *d_bad = nullptr, bad = 0;
+        SB_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
+        cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), stream);
+        int rc = e == cudaSuccess ? launch_check_cols(h->d_idx, h->num_e, b_rows, d_bad, stream) : 0;
+        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(stream);
+        cudaFree(d_bad);
+        if (rc) return rc;
+        SB_CUDA(e);
+        if (bad) {
+            set_error("CSR idx holds a column outside [0, %d)", b_rows);
+            return SPMM_B200_EINVAL;
+        }
+    }
+
     // split every row at the column-block boundaries (needs ascending columns inside a row; a graph
     // that is not sorted falls back to a single block)
     std::vector<int> split;

@@ -451,6 +451,18 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const int *ptr, const i
     }
 }
 
+// every column index must address a row of B: one pass over idx at plan time (a bad index would otherwise turn
+// into an out-of-bounds gather in every run)
+__global__ void __launch_bounds__(256) check_cols_kernel(const int *idx, long long nnz, int b_rows, int *bad) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    bool any = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int c = idx[i];
+        any |= c < 0 || c >= b_rows;
+    }
+    if (__any_sync(kFull, any) && (threadIdx.x & 31) == 0) atomicExch(bad, 1);
+}
+
 // one warp per light row: header at its slot, nonzeros at stride `groups` after it (the panel was preset to nops)
 __global__ void __launch_bounds__(256) build_lpanel_kernel(const int4 *light_desc, int n_light, int groups, const int *idx,
                                                            const float *val, int2 *lpanel) {
@@ -630,6 +642,14 @@ int resident_warps(int lanes, int vec, int tune, int block) {
         default: break;
     }
     return per_sm * sms;
+}
+
+int launch_check_cols(const int *d_idx, long long nnz, int b_rows, int *d_bad, cudaStream_t stream) {
+    if (nnz == 0) return 0;
+    const long long blocks = (nnz + 255) / 256;
+    check_cols_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(d_idx, nnz, b_rows, d_bad);
+    SB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,

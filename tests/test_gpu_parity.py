@@ -298,6 +298,36 @@ def test_call_protocol_and_idempotence():
     op.close()
 
 
+def test_preprocess_rejects_inconsistent_csr():
+    """Bad inputs come back as status codes with a message (the reference asserts / exits: data.cu:40-45, util.h:63-84)."""
+    ptr, idx = H.gen_named_graph("c0")
+    K = 32
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    bad_ptr = g.ptr.clone()
+    bad_ptr[-1] -= 1                                   # ptr[num_v] != num_e
+    op = H.SpMMB200(H.CSR(g.num_v, g.num_e, bad_ptr, g.idx, g.val), K)
+    with pytest.raises(H.SpmmB200Error) as e:
+        op.preprocess(vin, vout)
+    assert e.value.code == -1 and "ptr" in str(e.value)
+    op.close()
+    bad_idx = g.idx.clone()
+    bad_idx[12345] = g.num_v                           # column outside B
+    op = H.SpMMB200(H.CSR(g.num_v, g.num_e, g.ptr, bad_idx, g.val), K)
+    with pytest.raises(H.SpmmB200Error) as e:
+        op.preprocess(vin, vout)
+    assert e.value.code == -1 and "column" in str(e.value)
+    with pytest.raises(H.SpmmB200Error):
+        op.run(vin, vout)                              # no plan was built
+    op.close()
+    dec = g.ptr.clone()
+    dec[10], dec[11] = int(dec[11]), int(dec[10])      # a decreasing ptr
+    if int(dec[10]) != int(dec[11]):
+        op = H.SpMMB200(H.CSR(g.num_v, g.num_e, dec, g.idx, g.val), K)
+        with pytest.raises(H.SpmmB200Error):
+            op.preprocess(vin, vout)
+        op.close()
+
+
 @pytest.mark.parametrize("opts", [{}, {"col_blocks": 3}])
 def test_run_host_matches_device_run(opts):
     """Host-buffer call (with column blocks B is uploaded band by band while earlier passes compute)."""
