@@ -157,6 +157,17 @@ def test_engine_matches_oracle(shape, K, opts):
     op.close()
 
 
+@pytest.mark.parametrize("shape,K", [("collab", 32), ("ddi", 32), ("youtube", 32), ("am", 32), ("yelp", 32), ("wikikg2", 32),
+                                     ("collab", 256), ("ddi", 256), ("am", 256)])
+def test_dataset_shapes_strict_parity(shape, K):
+    """More of run_all.sh's dataset shapes under the strict bar (bit-exact whole rows, 1e-5 split rows), not only the
+    reference's 1e-2 criterion that tests/cpp/run_all.py applies to all 13."""
+    ptr, idx = H.gen_named_graph(shape)
+    op, g, vin, vout, got = run_engine(ptr, idx, K)
+    check_against_oracle(ptr, idx, K, op, g, vin, got)
+    op.close()
+
+
 def test_golden_vectors_through_engine(golden_dir):
     meta = json.load(open(os.path.join(golden_dir, "golden.json")))
     data = np.load(os.path.join(golden_dir, "golden.npz"))
