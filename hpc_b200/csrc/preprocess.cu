@@ -14,6 +14,10 @@
 //               [begin + floor(j*deg/nseg), begin + floor((j+1)*deg/nseg)),  j = 0..nseg-1
 //   panel     = the segments' {col, val} pairs back to back, each segment padded to an even
 //               number of entries (16-byte granules for the 1-D TMA copies), pad = {0, 0.0f}
+//   lpanel    = the rows of row_perm as a stream: per row a header {0x80000000 | row, 0} and its {col, val}
+//               entries, packed into equal-sized warp tasks by pack_light_host (rule stated there)
+//   column blocks: when B exceeds the L2 (auto_col_blocks), every row is split at the band boundaries
+//               (split[b][r]) and the whole plan above is built once per block over [split[b][r], split[b+1][r])
 #include <string.h>
 
 #include <algorithm>

@@ -11,6 +11,9 @@ independently written restatement of the plan's published definition:
   row_perm = non-heavy rows in order; heavy rows in order are cut into
   nseg = ceil(deg/seg_len) segments [begin + j*deg//nseg, begin + (j+1)*deg//nseg);
   panel = segments' (col, val-bits) pairs back to back, each padded to an even entry count.
+  lpanel / ltask = the rows of row_perm as a stream of header + entries, packed into equal-sized tasks
+  (pack_light); split / column blocks = rows cut at the boundaries of nb bands of B rows (split_rows),
+  one plan per band.
 """
 from __future__ import annotations
 
