@@ -168,7 +168,10 @@ class SpMMB200(SpMM):
             self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: the library may already be gone
+            pass
 
 
 def fill_normal(t: torch.Tensor, seed: int, stream_id: int, mean: float = 0.0, stddev: float = 0.1) -> torch.Tensor:
