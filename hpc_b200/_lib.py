@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspmm_b200.so")
+# SPMM_B200_LIB points at another build of the same library (tuning experiments); there is still no fallback.
+LIB_PATH = os.environ.get("SPMM_B200_LIB") or os.path.join(_HERE, "libspmm_b200.so")
 
 
 class PlanInfo(C.Structure):
