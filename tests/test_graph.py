@@ -170,3 +170,39 @@ def test_pack_light_host_matches_oracle():
                 assert len(np.unique(used)) == len(used) and used.max() < length
                 assert np.all(ltask[:, 0] % 2 == 0) and np.all((ltask[:, 1] * groups) % 2 == 0)
                 assert np.array_equal(ltask[1:, 0], (ltask[:, 0] + ltask[:, 1] * groups)[:-1])
+
+
+def test_property_based_plan_and_packing():
+    """hypothesis: random degree sequences / costs -> product == oracle, plus structural invariants."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(0, 700), min_size=0, max_size=300), st.integers(1, 300), st.booleans())
+    def plan_case(degs, seg_len, reorder):
+        ptr = np.concatenate([[0], np.cumsum(np.asarray(degs, np.int64))]).astype(np.int32)
+        nnz = int(ptr[-1])
+        idx = np.zeros(nnz, np.int32)
+        val = np.zeros(nnz, np.float32)
+        got = H.plan_host(ptr, 32, seg_len, reorder)
+        want = P.plan(ptr, idx, val, seg_len, reorder)
+        for k in ("row_perm", "heavy_rows", "heavy_seg0", "seg_desc"):
+            assert np.array_equal(got[k], want[k]), k
+        # every row appears exactly once; segments tile their rows
+        rows = np.concatenate([got["row_perm"], got["heavy_rows"]])
+        assert sorted(rows.tolist()) == list(range(len(degs)))
+        assert int(got["seg_desc"][:, 2].sum()) == int(sum(d for d in degs if d > seg_len))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 400), min_size=0, max_size=400), st.sampled_from([1, 2, 4, 8, 16, 32]), st.integers(1, 300))
+    def pack_case(costs, groups, steps):
+        cost = np.asarray(costs, np.int32)
+        dst, ltask, length = H.pack_light_host(cost, groups, steps)
+        odst, otask, olen = P.pack_light(cost, groups, steps)
+        assert np.array_equal(dst, odst) and np.array_equal(ltask, otask) and length == olen
+        if len(cost):
+            used = np.concatenate([d + np.arange(c) * groups for d, c in zip(dst, cost)])
+            assert len(np.unique(used)) == len(used) and used.max() < length and length % 2 == 0
+            assert int((ltask[:, 1] * groups).sum()) == length
+
+    plan_case()
+    pack_case()
