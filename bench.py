@@ -402,7 +402,7 @@ def run_b200(args):
 # dram__bytes_read.sum + dram__bytes_write.sum of spmm_kernel, per launch, from the `ncu --set full` captures
 # summarised in profiles/r01_ncu_summary.md (1 GPU). reddit_k256: mean of the 5 column-block passes of one step.
 NCU_TRAFFIC = {
-    "reddit_k256": int(778.08e6),                 # mean of the 5 column-block passes of one step (prof_reddit_r01d)
+    "reddit_k256": int(777.4e6),                  # mean of the 5 column-block passes of one step (prof_reddit_final)
     "products_k256": int(70.43e9 + 2.57e9),       # prof_products_k256_r01d
     "arxiv_k32": int(33.74e6 + 0.18e6),           # prof_arxiv_k32_r01d
     "arxiv_k256": int(599.96e6 + 119.85e6),       # prof_arxiv_k256_r01d
