@@ -22,7 +22,7 @@ class PlanInfo(C.Structure):
         ("seg_len", C.c_int), ("kslice", C.c_int), ("n_slices", C.c_int), ("block", C.c_int),
         ("n_light", C.c_int), ("n_heavy", C.c_int), ("n_seg", C.c_int),
         ("panel_len", C.c_longlong), ("lanes", C.c_int), ("vec", C.c_int),
-        ("n_ltask", C.c_int), ("lpanel_len", C.c_longlong), ("light_steps", C.c_int), ("reorder", C.c_int), ("resident_warps", C.c_int),
+        ("n_ltask", C.c_int), ("n_utask", C.c_int), ("lpanel_len", C.c_longlong), ("light_steps", C.c_int), ("reorder", C.c_int), ("resident_warps", C.c_int),
         ("n_col_blocks", C.c_int), ("col_begin", C.c_int), ("col_end", C.c_int),
     ]
 

@@ -262,6 +262,7 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info) {
     info->lanes = p.lanes;
     info->vec = p.vec;
     info->n_ltask = b.n_ltask;
+    info->n_utask = b.n_utask;
     info->lpanel_len = b.lpanel_len;
     info->light_steps = b.light_steps;
     info->resident_warps = (int)p.slots;
@@ -290,6 +291,7 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
         case 5: src = p.d_light_desc; want = sizeof(int4) * (size_t)p.n_light; break;
         case 6: src = p.d_seg_hrow; want = sizeof(int) * (size_t)p.n_seg; break;
         case 8: src = p.d_ltask; want = sizeof(int2) * (size_t)p.n_ltask; break;
+        case 10: src = p.d_utask; want = sizeof(int2) * (size_t)p.n_utask; break;
         case 9: src = p.d_lpanel; want = sizeof(int2) * (size_t)p.lpanel_len; break;
         case 7:
             src = pl.d_split;

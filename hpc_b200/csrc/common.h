@@ -45,9 +45,9 @@ struct RunArgs {
     // light rows
     const int4 *light_desc;   // {row, begin, deg, dst} in processing order (dst: its header's slot in lpanel)
     int n_light;
-    int light_tasks_per_slice;   // stream tasks per slice (= n_ltask)
-    const int2 *ltask;        // light stream tasks: {lpanel offset, steps per lane group}
-    int n_ltask;
+    const int2 *utask;        // warp tasks of one slice in scheduling order: {lpanel offset, steps per lane group}
+                              // for a light-stream task, {-1 - segment, 0} for a heavy segment
+    int n_utask;
     const int2 *lpanel;       // light rows as a stream: header {0x80000000|row, 0}, then {col, val}..., nop = {-1, -1}
     // heavy rows
     const SegDesc *seg_desc;
@@ -57,7 +57,6 @@ struct RunArgs {
     const int2 *panel;
     float *part;               // [n_seg][K] partial sums
     int n_seg;
-    long long heavy_tasks;     // n_seg * n_slices
     int accumulate;            // 1: continue the chains from vout (column blocks after the first)
     // stacked-layer epilogue: finished rows also go to every rank's copy of the next layer's B
     int n_gather;              // 0 = off
@@ -74,6 +73,8 @@ struct BlockPlan {
     int *d_row_perm = nullptr;
     int4 *d_light_desc = nullptr;
     int2 *d_ltask = nullptr;
+    int2 *d_utask = nullptr;
+    int n_utask = 0;
     int2 *d_lpanel = nullptr;
     int n_ltask = 0;
     int light_steps = 0;

@@ -32,6 +32,7 @@ void free_plan(Plan &p) {
         cudaFree(b.d_row_perm);
         cudaFree(b.d_light_desc);
         cudaFree(b.d_ltask);
+        cudaFree(b.d_utask);
         cudaFree(b.d_lpanel);
         cudaFree(b.d_heavy_rows);
         cudaFree(b.d_heavy_seg0);
@@ -270,11 +271,41 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
     }
     bp.n_ltask = (int)ltasks.size();
     bp.lpanel_len = lpanel_len;
+
+    // Scheduling order of the warp tasks. Bucketed rows: heavy segments (the longest rows) first, then the light
+    // tasks. Natural order: light tasks and heavy segments merged by the row they start with, so that a heavy row
+    // runs next to its neighbours (whose B rows it shares in L2) instead of ahead of everything.
+    std::vector<int2> utask;
+    utask.reserve(ltasks.size() + segs.size());
+    if (reorder == 0 && !p.scalar) {
+        size_t li = 0, first_i = 0;   // first_i: index in row_perm of the first row of light task li
+        size_t si = 0;
+        auto light_first_row = [&](size_t t) {
+            while (first_i < (size_t)bp.n_light && dst[first_i] < ltasks[t].x) ++first_i;
+            return first_i < (size_t)bp.n_light ? row_perm[first_i] : 0x7fffffff;
+        };
+        while (li < ltasks.size() || si < segs.size()) {
+            const int lrow = li < ltasks.size() ? light_first_row(li) : 0x7fffffff;
+            const int hrow = si < segs.size() ? segs[si].row : 0x7fffffff;
+            if (si < segs.size() && hrow < lrow) {
+                utask.push_back(make_int2(-1 - (int)si, 0));
+                ++si;
+            } else {
+                utask.push_back(ltasks[li]);
+                ++li;
+            }
+        }
+    } else {
+        for (size_t si = 0; si < segs.size(); ++si) utask.push_back(make_int2(-1 - (int)si, 0));
+        for (const int2 &t : ltasks) utask.push_back(t);
+    }
+    bp.n_utask = (int)utask.size();
     std::vector<int> seg_hrow((size_t)bp.n_seg);
     for (int hr = 0; hr < bp.n_heavy; ++hr)
         for (int sgm = heavy_seg0[hr]; sgm < heavy_seg0[hr + 1]; ++sgm) seg_hrow[sgm] = hr;
     if ((rc = upload((void **)&bp.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
     if ((rc = upload((void **)&bp.d_light_desc, light.data(), sizeof(int4) * light.size()))) return rc;
+    if ((rc = upload((void **)&bp.d_utask, utask.data(), sizeof(int2) * utask.size()))) return rc;
     if (bp.n_ltask > 0) {
         if ((rc = upload((void **)&bp.d_ltask, ltasks.data(), sizeof(int2) * ltasks.size()))) return rc;
         SB_CUDA(cudaMalloc((void **)&bp.d_lpanel, sizeof(int2) * (size_t)lpanel_len));

@@ -133,16 +133,11 @@ struct Tune {
 // CSR order (bit-exact), but gathers stay in flight across row boundaries and no load depends on a
 // per-row descriptor.
 template <int LANES, int VEC, int TUNE, bool FULL>
-__device__ __forceinline__ void light_stream(const RunArgs &a, long long gw, int lane, int2 *buf, uint64_t *bars) {
+__device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 td, int lane, int2 *buf, uint64_t *bars) {
     constexpr int GROUPS = 32 / LANES;
     constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
     const int g = lane / LANES;
-    if (a.n_ltask == 0) return;   // every row is heavy: the spare warps of the last CTA have nothing to do
-    const int slice = (int)(gw / a.n_ltask);
-    if (slice >= a.n_slices) return;
-    const int task = (int)(gw - (long long)slice * a.n_ltask);
-    const int2 td = __ldg(a.ltask + task);
     const int len = td.y * GROUPS;
     const int nchunks = (len + kChunk - 1) / kChunk;
     const int2 *src = a.lpanel + td.x;
@@ -247,13 +242,11 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, long long gw, int
 }
 
 template <int LANES, int VEC, int TUNE, bool FULL>
-__device__ __forceinline__ void heavy_segment(const RunArgs &a, long long gw, int lane, int2 *buf, uint64_t *bars) {
+__device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int seg, int lane, int2 *buf, uint64_t *bars) {
     constexpr int GROUPS = 32 / LANES;
     constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
     const int g = lane / LANES;
-    const int slice = (int)(gw / a.n_seg);
-    const int seg = (int)(gw - (long long)slice * a.n_seg);
     const SegDesc d = a.seg_desc[seg];
     const int nchunks = (d.len + kChunk - 1) / kChunk;
     const int2 *src = a.panel + d.panel_off;
@@ -378,17 +371,16 @@ __global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_kernel(
     const int lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
     const long long gw = (long long)blockIdx.x * nwarps + warp;
-    if (gw < a.heavy_tasks) {
-        int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
-        uint64_t *bars =
-            reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages;
-        heavy_segment<LANES, VEC, TUNE, FULL>(a, gw, lane, buf, bars);
-    } else {
-        int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
-        uint64_t *bars =
-            reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages;
-        light_stream<LANES, VEC, TUNE, FULL>(a, gw - a.heavy_tasks, lane, buf, bars);
-    }
+    // one task list per feature slice: {lpanel offset, steps} for a light-stream task, {-1 - segment, 0} for a heavy
+    // segment, in the order the plan wants them scheduled
+    const int slice = (int)(gw / a.n_utask);
+    if (slice >= a.n_slices) return;
+    const int2 td = __ldg(a.utask + (gw - (long long)slice * a.n_utask));
+    int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
+    uint64_t *bars =
+        reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages;
+    if (td.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a, slice, -1 - td.x, lane, buf, bars);
+    else light_stream<LANES, VEC, TUNE, FULL>(a, slice, td, lane, buf, bars);
 }
 
 // K % 4 != 0: scalar lanes over the feature columns, one warp per row, same in-order chain.
@@ -529,7 +521,7 @@ __global__ void __launch_bounds__(256) valid_kernel(const float *y, const float 
 template <int LANES, int VEC, int TUNE, bool FULL>
 void launch_tuned(const RunArgs &a, int block, cudaStream_t stream) {
     const int warps = block / 32;
-    const long long tasks = a.heavy_tasks + (long long)a.light_tasks_per_slice * a.n_slices;
+    const long long tasks = (long long)a.n_utask * a.n_slices;
     const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
     spmm_kernel<LANES, VEC, TUNE, FULL><<<(unsigned)((tasks + warps - 1) / warps), block, smem, stream>>>(a);
 }
@@ -569,7 +561,7 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
     for (int blk = 0; blk < p.n_col_blocks; ++blk) {
         const BlockPlan &bp = p.blocks[blk];
         if (band_ready) SB_CUDA(cudaStreamWaitEvent(stream, band_ready[blk], 0));
-        if (blk > 0 && bp.n_light == 0 && bp.n_seg == 0) continue;
+        if (bp.n_light == 0 && bp.n_seg == 0) continue;
         RunArgs a;
         a.idx = h->d_idx;
         a.val = h->d_val;
@@ -580,9 +572,9 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         a.n_slices = p.n_slices;
         a.light_desc = bp.d_light_desc;
         a.n_light = bp.n_light;
-        a.ltask = bp.d_ltask;
+        a.utask = bp.d_utask;
+        a.n_utask = bp.n_utask;
         a.lpanel = bp.d_lpanel;
-        a.n_ltask = bp.n_ltask;
         a.seg_desc = bp.d_seg_desc;
         a.seg_hrow = bp.d_seg_hrow;
         a.seg_count = bp.d_seg_count;
@@ -590,7 +582,6 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         a.part = bp.d_part;
         a.n_seg = bp.n_seg;
         a.heavy_seg0 = bp.d_heavy_seg0;
-        a.heavy_tasks = (long long)bp.n_seg * p.n_slices;
         a.accumulate = blk > 0;
         const bool last = blk + 1 == p.n_col_blocks;   // only the last pass produces final rows
         a.n_gather = last ? h->n_gather : 0;
@@ -598,12 +589,10 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         a.gather_mc = h->gather_mc;
         a.gather_row0 = h->gather_row0;
         if (p.scalar) {
-            a.light_tasks_per_slice = a.n_light;
             const int warps = p.block / 32;
             spmm_scalar_kernel<<<(unsigned)((a.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
         } else {
             const bool full = h->feat % (p.lanes * p.vec * 4) == 0 && p.kslice == p.lanes * p.vec * 4;
-            a.light_tasks_per_slice = a.n_ltask;
             switch (p.lanes * 10 + p.vec) {
                 case 11: launch_shape<1, 1>(a, p.block, p.tune, full, stream); break;
                 case 21: launch_shape<2, 1>(a, p.block, p.tune, full, stream); break;

@@ -142,7 +142,8 @@ class SpMMB200(SpMM):
                                (3, "seg_desc", info["n_seg"] * 4), (4, "panel", info["panel_len"] * 2),
                                (5, "light_desc", info["n_light"] * 4), (6, "seg_hrow", info["n_seg"]),
                                (7, "split", (nb + 1) * self.num_v if nb > 1 else 0),
-                               (8, "ltask", info["n_ltask"] * 2), (9, "lpanel", info["lpanel_len"] * 2)):
+                               (8, "ltask", info["n_ltask"] * 2), (9, "lpanel", info["lpanel_len"] * 2),
+                               (10, "utask", info["n_utask"] * 2)):
             a = np.empty(n, dtype=np.int32)
             check(lib.spmm_b200_plan_copy(self._h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
             out[name] = a
@@ -150,6 +151,7 @@ class SpMMB200(SpMM):
         out["panel"] = out["panel"].reshape(-1, 2)
         out["light_desc"] = out["light_desc"].reshape(-1, 4)
         out["ltask"] = out["ltask"].reshape(-1, 2)
+        out["utask"] = out["utask"].reshape(-1, 2)
         out["lpanel"] = out["lpanel"].reshape(-1, 2)
         if nb > 1:
             out["split"] = out["split"].reshape(nb + 1, self.num_v)

@@ -113,6 +113,7 @@ typedef struct {
     int lanes;          /* lanes cooperating on one row in the light kernel */
     int vec;            /* float4 per lane */
     int n_ltask;        /* light-stream tasks (one warp each) */
+    int n_utask;        /* all warp tasks of one feature slice: n_ltask + n_seg */
     long long lpanel_len; /* entries in the light stream panel */
     int light_steps;    /* target entries per lane group and task (selected block) */
     int reorder;        /* row order in effect for the selected block: 1 bucketed, 0 natural */
@@ -136,6 +137,9 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *   5 light_desc int32[n_light*4]   {row, first CSR position, nonzeros, slot of its header in lpanel} per light
  *                                   row, same order as row_perm
  *   8 ltask      int32[n_ltask*2]   {lpanel offset, steps per lane group} per light-stream task
+ *  10 utask      int32[n_utask*2]   the warp tasks of one feature slice in scheduling order: a light-stream task as in
+ *                                   ltask, a heavy segment as {-1 - segment, 0}. Bucketed rows: segments first, then the
+ *                                   light tasks; natural order: merged by the row each task starts with
  *   9 lpanel     int32[lpanel_len*2] light rows as a stream of {x, y} entries: header {0x80000000|row, 0},
  *                                   nonzero {col, float bits of val}, nop {-1, -1}; within a task, entry j of
  *                                   lane group g sits at offset + j*groups + g

@@ -205,6 +205,23 @@ def light_stream(plan_dict, idx, val, groups: int, steps: int) -> dict:
     return {"light_desc": ld, "ltask": tasks, "lpanel": panel}
 
 
+def unified_tasks(plan_dict, stream_dict, reorder: bool) -> np.ndarray:
+    """Scheduling order of the warp tasks of one slice: (lpanel offset, steps) for a light task, (-1 - segment, 0) for
+    a heavy segment. Bucketed rows: all segments, then the light tasks. Natural order: merged by first row (a light
+    task's first row is the row whose header sits at its offset)."""
+    ltask = stream_dict["ltask"]
+    nseg = len(plan_dict["seg_desc"])
+    heavy = [(-1 - s, 0) for s in range(nseg)]
+    light = [tuple(int(x) for x in t) for t in ltask]
+    if reorder:
+        return np.asarray(heavy + light, np.int32).reshape(-1, 2)
+    ld = stream_dict["light_desc"]
+    first_row = {int(d): int(r) for r, _, _, d in ld}          # header slot -> row
+    keyed = [(first_row[t[0]], 1, t) for t in light] + [(int(plan_dict["seg_desc"][s][0]), 0, heavy[s]) for s in range(nseg)]
+    keyed.sort(key=lambda k: (k[0], k[1]))                     # stable: a row's segments stay in order
+    return np.asarray([k[2] for k in keyed], np.int32).reshape(-1, 2)
+
+
 def student_split_check(ptr, tasks) -> bool:
     """With seg_len = 256 a row of deg d yields ceil(d/256) pieces in both schemes
     (spmm_opt.cu:46 steps by kBatchSize; the plan balances the same number of pieces)."""

@@ -357,7 +357,7 @@ def test_run_host_matches_device_run(opts):
 
 # ---- integer paths: bit-exact -----------------------------------------------------------------------
 
-@pytest.mark.parametrize("shape,seg_len,reorder", [("c0", 0, 1), ("c0", 16, 1), ("c0", 16, 0), ("arxiv", 0, 1), ("arxiv", 100, 1)])
+@pytest.mark.parametrize("shape,seg_len,reorder", [("c0", 0, 1), ("c0", 16, 1), ("c0", 16, 0), ("arxiv", 0, 1), ("arxiv", 100, 1), ("arxiv", 0, 0)])
 def test_plan_matches_oracle(shape, seg_len, reorder):
     ptr, idx = H.gen_named_graph(shape)
     g, vin, vout = dev_inputs(ptr, idx, 32)
@@ -369,6 +369,8 @@ def test_plan_matches_oracle(shape, seg_len, reorder):
     assert info["seg_len"] == (seg_len or P.auto_seg_len(len(idx), 32))
     assert info["kslice"] == P.auto_kslice(g.num_v, 32)
     want.update(P.light_stream(want, idx, g.val.cpu().numpy(), 32 // info["lanes"], info["light_steps"]))
+    want["utask"] = P.unified_tasks(want, want, bool(reorder))
+    assert np.array_equal(got["utask"], want["utask"]) and info["n_utask"] == info["n_ltask"] + info["n_seg"]
     total = int(want["light_desc"][:, 2].astype(np.int64).sum()) + len(want["light_desc"])
     assert info["light_steps"] == P.auto_light_steps(32 // info["lanes"], total, info["resident_warps"], len(want["seg_desc"]))
     assert info["resident_warps"] >= 148 * 8

@@ -95,7 +95,6 @@ def bench(name, K, optlist, iters=10):
 
 print(torch.cuda.get_device_name(0), flush=True)
 if mode in ("quick", "full"):
-    parity("arxiv", 256, kslice=128)
-    bench("arxiv", 256, [{}, {"kslice": 128}, {"kslice": 64}, {"kslice": 128, "tune": 1}], iters=10)
-    bench("collab", 256, [{}, {"kslice": 128}], iters=10)
-    bench("youtube", 256, [{}, {"kslice": 128}], iters=10)
+    parity("arxiv", 256, reorder=0)
+    for g, K in (("products", 256), ("reddit", 256), ("citation", 256), ("amazon_cogdl", 256), ("arxiv", 256), ("arxiv", 32)):
+        bench(g, K, [{}, {"reorder": 1}, {"reorder": 0}], iters=10 if g == "arxiv" else 5)
