@@ -120,7 +120,8 @@ def cpu_sample(ptr, idx, k, seconds, nthreads=0):
     val = O.fill_normal(nnz, SEED, 1)
     b = O.fill_normal(m * k, SEED, 2)
     out = np.zeros(m * k, np.float32)
-    cores = nthreads or O.num_threads()
+    # all the cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)
+    cores = nthreads or max(O.num_threads(), len(os.sched_getaffinity(0)))
 
     def run(rows):
         t = time.perf_counter()
@@ -151,6 +152,7 @@ def run_reference(args):
     if rank != 0:
         return
     import hpc_b200 as H  # host-side graph generator only (no GPU work on this arm)
+    H.set_host_threads(len(os.sched_getaffinity(0)))
     shape, k = WORKLOADS[args.workload]
     ptr, idx = H.gen_named_graph(shape, SEED)
     m, nnz = len(ptr) - 1, len(idx)
@@ -248,6 +250,7 @@ def run_b200(args):
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
     shape, k = WORKLOADS[args.workload]
+    H.set_host_threads(max(1, len(os.sched_getaffinity(0)) // world))   # the generator's share of the host cores
     ptr, idx = H.gen_named_graph(shape, SEED)
     m, nnz = len(ptr) - 1, len(idx)
     deg = np.diff(ptr)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "spmm_b200_valid": (_I, [_P, _P, _LL, C.POINTER(_LL), _P]),
     "spmm_b200_gen_graph": (_I, [_I, _LL, _I, _I, _I, _I, _I, _U64, _P, _P]),
     "spmm_b200_gen_degrees": (_I, [_I, _LL, _I, _I, _I, _U64, _P]),
+    "spmm_b200_set_host_threads": (_I, [_I]),
     "spmm_b200_load_graph": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), _P, _P]),
     "spmm_b200_write_graph": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _I]),
     "spmm_b200_partition_rows": (_I, [_P, _I, _I, _P]),

@@ -238,6 +238,19 @@ extern "C" int spmm_b200_gen_graph(int num_v, long long nnz, int max_deg, int ta
     return 0;
 }
 
+// Host threads for the OpenMP parts of this library (graph generator). torchrun exports OMP_NUM_THREADS=1 to its
+// workers; a caller that knows its share of the cores can override that here.
+extern "C" int spmm_b200_set_host_threads(int n) {
+    if (n < 1) {
+        set_error("set_host_threads: need n >= 1");
+        return SPMM_B200_EINVAL;
+    }
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#endif
+    return 0;
+}
+
 // ---- reference graph files (PA4/handout/src/data.cu:3-66) -------------------------------------
 
 static bool file_exists(const std::string &p) {

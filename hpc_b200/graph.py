@@ -44,6 +44,11 @@ def _ip(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def set_host_threads(n: int) -> None:
+    """OpenMP threads for the generator (torchrun sets OMP_NUM_THREADS=1 in its workers)."""
+    check(lib.spmm_b200_set_host_threads(int(n)))
+
+
 def gen_degrees(num_v, nnz, max_deg, tail_k=2, zero_ppm=0, seed=123) -> np.ndarray:
     deg = np.empty(num_v, dtype=np.int32)
     check(lib.spmm_b200_gen_degrees(num_v, nnz, max_deg, tail_k, zero_ppm, seed, _ip(deg)))

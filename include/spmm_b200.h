@@ -194,6 +194,9 @@ int spmm_b200_gen_graph(int num_v, long long nnz, int max_deg, int tail_k, int z
 int spmm_b200_gen_degrees(int num_v, long long nnz, int max_deg, int tail_k, int zero_ppm,
                           uint64_t seed, int *deg);
 
+/* Host threads used by the OpenMP parts of the library (the generator above); overrides OMP_NUM_THREADS. */
+int spmm_b200_set_host_threads(int n);
+
 /* load_graph (PA4/handout/src/data.cu:3-66): <dir>/<dset>.config ("num_v num_e"),
  * <dset>.graph (text: num_v+1 ptr ints then num_e idx ints), binary caches
  * <dset>.graph.ptrdump / .edgedump (int32), written on first text read.
