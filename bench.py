@@ -406,14 +406,15 @@ def run_b200(args):
 # summarised in profiles/r01_ncu_summary.md (1 GPU). reddit_k256: mean of the 5 column-block passes of one step.
 NCU_TRAFFIC = {
     "reddit_k256": int(777.4e6),                  # mean of the 5 column-block passes of one step (prof_reddit_final)
-    "products_k256": int(70.43e9 + 2.57e9),       # prof_products_k256_r01d
+    "products_k256": int(67.02e9 + 2.58e9),       # prof_products_k256_final
+    "reddit_k32": int(1.176e9 + 34.6e6),          # prof_reddit_k32_final
     "arxiv_k32": int(33.74e6 + 0.18e6),           # prof_arxiv_k32_r01d
     "arxiv_k256": int(599.96e6 + 119.85e6),       # prof_arxiv_k256_r01d
 }
 
 
 # lts__t_sector_hit_rate.pct of the same captures: the L2 hit rate, essentially that of the B-row gathers
-NCU_L2_HIT_PCT = {"reddit_k256": 94.9, "products_k256": 33.2, "arxiv_k32": 55.2, "arxiv_k256": 32.0}
+NCU_L2_HIT_PCT = {"reddit_k256": 94.9, "products_k256": 35.6, "reddit_k32": 86.6, "arxiv_k32": 55.2, "arxiv_k256": 32.0}
 
 # What actually binds each workload (ncu, profiles/r01_ncu_summary.md). "l2_fabric": bytes gathered L2 -> SM per second
 # against the fabric rate at which ncu shows lts2xbar 100 % busy (19.58 TB/s at 84.6 % => 23.1 TB/s). "hbm_traffic": the
