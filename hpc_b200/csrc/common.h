@@ -136,9 +136,9 @@ int resident_warps(int lanes, int vec, int tune, int block);
 int launch_check_cols(const int *d_idx, long long nnz, int b_rows, int *d_bad, cudaStream_t stream);
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
                       int *d_split, int *d_unsorted, cudaStream_t stream);
-int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, const int *d_idx, const float *d_val,
+int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, int k4, const int *d_idx, const float *d_val,
                         int2 *d_lpanel, cudaStream_t stream);
-int launch_build_panel(const SegDesc *d_seg, int n_seg, const int *d_idx, const float *d_val,
+int launch_build_panel(const SegDesc *d_seg, int n_seg, int k4, int pad, const int *d_idx, const float *d_val,
                        int2 *d_panel, cudaStream_t stream);
 int launch_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream_id, float mean,
                        float stddev, cudaStream_t stream);

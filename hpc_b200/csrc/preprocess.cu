@@ -12,8 +12,8 @@
 //   row_perm  = the non-heavy rows in that order
 //   heavy rows, in that order, are cut into nseg = ceil(deg/seg_len) nnz-balanced segments
 //               [begin + floor(j*deg/nseg), begin + floor((j+1)*deg/nseg)),  j = 0..nseg-1
-//   panel     = the segments' {col, val} pairs back to back, each segment padded to an even
-//               number of entries (16-byte granules for the 1-D TMA copies), pad = {0, 0.0f}
+//   panel     = the segments' {col * K/4, val} pairs back to back, each segment padded with nop entries {-1, 0} to a
+//               multiple of 4 * (32 / lanes) entries (whole gather batches, 16-byte granules for the TMA copies)
 //   lpanel    = the rows of row_perm as a stream: per row a header {0x80000000 | row, 0} and its {col, val}
 //               entries, packed into equal-sized warp tasks by pack_light_host (rule stated there)
 //   column blocks: when B exceeds the L2 (auto_col_blocks), every row is split at the band boundaries
@@ -89,7 +89,9 @@ int auto_col_blocks(long long b_rows, int feat, long long nnz, int num_v) {
 // Host-only core of the plan (also exported as spmm_b200_plan_host for CPU-side tests).
 // Row r owns CSR positions [rb[r], re[r]) (rb = ptr, re = ptr + 1 for the whole matrix; a column block
 // passes its own bounds). skip_empty drops rows with no nonzero in the block (passes after the first).
-int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder, int skip_empty,
+// `pad`: every segment's panel span is padded (with nop entries) to a multiple of `pad` entries: 4 gather steps
+// of all lane groups, so the kernel reads whole batches without bounds checks.
+int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder, int skip_empty, int pad,
                    std::vector<int> &row_perm, std::vector<int> &heavy_rows, std::vector<int> &heavy_seg0,
                    std::vector<SegDesc> &segs, long long *panel_len_out) {
     // stable counting sort by bucket, descending
@@ -142,7 +144,7 @@ int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder
             s.len = e - b;
             s.nnz_begin = b;
             segs.push_back(s);
-            panel_len += (s.len + 1) & ~1;
+            panel_len += (s.len + pad - 1) / pad * pad;
         }
     }
     if (!heavy_rows.empty()) heavy_seg0.push_back((int)segs.size());
@@ -158,8 +160,8 @@ int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder
 // then its nonzeros). A task has `groups` lanes (one per lane group of the warp). A row goes to the least-filled
 // lane of the current task (lowest index on ties); if that lane is non-empty and the row would take it past
 // `steps` entries, the task is closed and the row opens the next one. A task's lanes are interleaved in the
-// panel — entry j of lane g sits at off + j*groups + g — and padded with nops to the longest lane (to an even
-// length when groups == 1, so every task starts on a 16-byte boundary).
+// panel — entry j of lane g sits at off + j*groups + g — and padded with nops to the longest lane rounded up to a
+// multiple of 4 steps (whole gather batches; it also keeps every task on a 16-byte boundary).
 long long pack_light_host(const int *cost, int n, int groups, int steps, int *dst, std::vector<int2> &tasks) {
     tasks.clear();
     std::vector<int> fill((size_t)groups, 0);
@@ -167,7 +169,7 @@ long long pack_light_host(const int *cost, int n, int groups, int steps, int *ds
     auto close_task = [&]() {
         int mx = 0;
         for (int x : fill) mx = std::max(mx, x);
-        if (groups == 1 && (mx & 1)) ++mx;
+        mx = (mx + 3) & ~3;   // whole batches of 4 steps: the kernel reads a task without bounds checks
         tasks.push_back(make_int2((int)off, mx));
         off += (long long)mx * groups;
         std::fill(fill.begin(), fill.end(), 0);
@@ -230,7 +232,8 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
         reorder = (p.lanes == 32 && p.slots > 0 && total >= 8ll * p.slots * 64) ? 0 : 1;
     }
     bp.reorder = reorder;
-    int rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, row_perm, heavy_rows, heavy_seg0,
+    const int pad = p.scalar ? 2 : 4 * (32 / p.lanes);
+    int rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, pad, row_perm, heavy_rows, heavy_seg0,
                             segs, &panel_len);
     if (rc) return rc;
     bp.n_light = (int)row_perm.size();
@@ -310,7 +313,7 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
         if ((rc = upload((void **)&bp.d_ltask, ltasks.data(), sizeof(int2) * ltasks.size()))) return rc;
         SB_CUDA(cudaMalloc((void **)&bp.d_lpanel, sizeof(int2) * (size_t)lpanel_len));
         SB_CUDA(cudaMemsetAsync(bp.d_lpanel, 0xFF, sizeof(int2) * (size_t)lpanel_len, stream));   // nop entries
-        if ((rc = launch_build_lpanel(bp.d_light_desc, bp.n_light, groups, h->d_idx, h->d_val, bp.d_lpanel, stream)))
+        if ((rc = launch_build_lpanel(bp.d_light_desc, bp.n_light, groups, K / 4, h->d_idx, h->d_val, bp.d_lpanel, stream)))
             return rc;
     }
     if (bp.n_heavy > 0) {
@@ -323,7 +326,7 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
         if ((rc = upload((void **)&bp.d_seg_desc, segs.data(), sizeof(SegDesc) * segs.size()))) return rc;
         SB_CUDA(cudaMalloc((void **)&bp.d_panel, sizeof(int2) * (size_t)panel_len));
         SB_CUDA(cudaMalloc((void **)&bp.d_part, sizeof(float) * (size_t)bp.n_seg * K));
-        if ((rc = launch_build_panel(bp.d_seg_desc, bp.n_seg, h->d_idx, h->d_val, bp.d_panel, stream))) return rc;
+        if ((rc = launch_build_panel(bp.d_seg_desc, bp.n_seg, K / 4, pad, h->d_idx, h->d_val, bp.d_panel, stream))) return rc;
     }
     SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
     return 0;
@@ -348,6 +351,10 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     p.light_steps = h->opt_light_steps > 0 ? (int)h->opt_light_steps : 0;
     p.slots = p.scalar ? 0 : resident_warps(p.lanes, p.vec, p.tune, p.block);
     if (p.scalar) p.seg_len = 0x7fffffff;   // scalar fallback keeps every row whole
+    if (!p.scalar && (long long)b_rows * (K / 4) > 0x7fffffffll) {
+        set_error("B is too large for 32-bit row offsets: b_rows * feat_in / 4 = %lld >= 2^31", (long long)b_rows * (K / 4));
+        return SPMM_B200_EINVAL;
+    }
     int nb = h->opt_col_blocks > 0 ? (int)h->opt_col_blocks : auto_col_blocks(b_rows, K, h->num_e, M);
     if (p.scalar || M == 0 || nb < 1) nb = 1;
     if (nb > b_rows) nb = b_rows > 0 ? b_rows : 1;
@@ -434,15 +441,14 @@ extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, int feat_in, lon
         set_error("spmm_b200_plan_host: bad arguments");
         return SPMM_B200_EINVAL;
     }
-    if (seg_len <= 0) {
-        int lanes = 32, vec = 1;
-        if (feat_in > 0 && feat_in % 4 == 0) shape_for_kslice(auto_kslice(num_v, feat_in), &lanes, &vec);
-        seg_len = (feat_in % 4 != 0) ? 0x7fffffffll : auto_seg_len(h_ptr[num_v], lanes);
-    }
+    int lanes = 32, vec = 1;
+    if (feat_in > 0 && feat_in % 4 == 0) shape_for_kslice(auto_kslice(num_v, feat_in), &lanes, &vec);
+    if (seg_len <= 0) seg_len = (feat_in % 4 != 0) ? 0x7fffffffll : auto_seg_len(h_ptr[num_v], lanes);
+    const int pad = (feat_in % 4 != 0) ? 2 : 4 * (32 / lanes);
     if (seg_len > 0x7fffffffll) seg_len = 0x7fffffffll;
     std::vector<int> rp, hr, hs;
     std::vector<SegDesc> segs;
-    int rc = plan_rows_host(h_ptr, h_ptr + 1, num_v, (int)seg_len, reorder, 0, rp, hr, hs, segs, panel_len);
+    int rc = plan_rows_host(h_ptr, h_ptr + 1, num_v, (int)seg_len, reorder, 0, pad, rp, hr, hs, segs, panel_len);
     if (rc) return rc;
     *n_light = (int)rp.size();
     *n_heavy = (int)hr.size();

@@ -44,9 +44,6 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
-__device__ __forceinline__ float4 ld_b_row(const float *p) {
-    return __ldg(reinterpret_cast<const float4 *>(p));
-}
 __device__ __forceinline__ void st_c_row(float *p, const float4 &v) {
     __stcs(reinterpret_cast<float4 *>(p), v);
 }
@@ -162,7 +159,8 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 t
     const int K = a.feat;
     const int col0 = slice * a.kslice + l * 4;
     const int col_end = min(K, (slice + 1) * a.kslice);
-    const float *bbase = a.vin + col0;
+    // panel entries carry the B row's offset in float4 units (col * K/4), so a gather address is one multiply-add
+    const float4 *bbase = reinterpret_cast<const float4 *>(a.vin + col0);
     float4 acc[VEC];
     bool colok[VEC];
 #pragma unroll
@@ -189,14 +187,12 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 t
             int2 cv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int t = t0 + u * GROUPS + g;
-                cv[u] = make_int2(-1, 0);
-                if (t < n) cv[u] = e[t];
+                cv[u] = e[t0 + u * GROUPS + g];   // in range: a task is padded to a multiple of 4 steps
                 if (cv[u].x >= 0) {
-                    const float *brow = bbase + (size_t)cv[u].x * K;
+                    const float4 *brow = bbase + (unsigned)cv[u].x;
 #pragma unroll
                     for (int v = 0; v < VEC; ++v)
-                        if (colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
+                        if (colok[v]) b[u][v] = __ldg(brow + v * LANES);
                 }
             }
             bool hdr = false;
@@ -248,7 +244,8 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
     const int l = lane % LANES;
     const int g = lane / LANES;
     const SegDesc d = a.seg_desc[seg];
-    const int nchunks = (d.len + kChunk - 1) / kChunk;
+    const int plen = (d.len + 4 * GROUPS - 1) / (4 * GROUPS) * (4 * GROUPS);   // the panel span, padded with nops
+    const int nchunks = (plen + kChunk - 1) / kChunk;
     const int2 *src = a.panel + d.panel_off;
 
     if (lane == 0) {
@@ -259,8 +256,7 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
     __syncwarp();
     auto issue = [&](int k) {
         const int s = k % kStages;
-        const int n = min(kChunk, d.len - k * kChunk);
-        const uint32_t bytes = (uint32_t)((n + 1) & ~1) * 8u;   // panel is padded to 16 B
+        const uint32_t bytes = (uint32_t)min(kChunk, plen - k * kChunk) * 8u;
         mbar_expect_tx(&bars[s], bytes);
         tma_bulk_g2s(buf + s * kChunk, src + (size_t)k * kChunk, bytes, &bars[s]);
     };
@@ -272,7 +268,8 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
     const int K = a.feat;
     const int col0 = slice * a.kslice + l * 4;
     const int col_end = min(K, (slice + 1) * a.kslice);
-    const float *bbase = a.vin + col0;
+    // panel entries carry the B row's offset in float4 units (col * K/4), so a gather address is one multiply-add
+    const float4 *bbase = reinterpret_cast<const float4 *>(a.vin + col0);
     float4 acc[VEC];
     bool colok[VEC];
 #pragma unroll
@@ -284,7 +281,7 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
     for (int k = 0; k < nchunks; ++k) {
         const int s = k % kStages;
         mbar_wait(&bars[s], (uint32_t)(k / kStages) & 1u);
-        const int n = min(kChunk, d.len - k * kChunk);
+        const int n = min(kChunk, plen - k * kChunk);
         const int2 *e = buf + s * kChunk;
         for (int t0 = 0; t0 < n; t0 += GROUPS * U) {
             float4 b[U][VEC];
@@ -292,15 +289,13 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
             bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int t = t0 + u * GROUPS + g;
-                ok[u] = t < n;
-                int2 cv = make_int2(0, 0);
-                if (ok[u]) cv = e[t];
+                const int2 cv = e[t0 + u * GROUPS + g];   // in range: the span is padded to whole batches
+                ok[u] = cv.x >= 0;                        // nop entries are {-1, 0}
                 wt[u] = __int_as_float(cv.y);
-                const float *brow = bbase + (size_t)cv.x * K;
+                const float4 *brow = bbase + (unsigned)cv.x;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) b[u][v] = ld_b_row(brow + v * LANES * 4);
+                    if (ok[u] && colok[v]) b[u][v] = __ldg(brow + v * LANES);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -456,28 +451,28 @@ __global__ void __launch_bounds__(256) check_cols_kernel(const int *idx, long lo
 }
 
 // one warp per light row: header at its slot, nonzeros at stride `groups` after it (the panel was preset to nops)
-__global__ void __launch_bounds__(256) build_lpanel_kernel(const int4 *light_desc, int n_light, int groups, const int *idx,
-                                                           const float *val, int2 *lpanel) {
+__global__ void __launch_bounds__(256) build_lpanel_kernel(const int4 *light_desc, int n_light, int groups, int k4,
+                                                           const int *idx, const float *val, int2 *lpanel) {
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= n_light) return;
     const int4 d = light_desc[gw];   // {row, begin, deg, dst}
     if (lane == 0) lpanel[d.w] = make_int2((int)(0x80000000u | (unsigned)d.x), 0);
     for (int t = lane; t < d.z; t += 32)
-        lpanel[(size_t)d.w + (size_t)(1 + t) * groups] = make_int2(idx[d.y + t], __float_as_int(val[d.y + t]));
+        lpanel[(size_t)d.w + (size_t)(1 + t) * groups] = make_int2(idx[d.y + t] * k4, __float_as_int(val[d.y + t]));
 }
 
-// one warp per segment: gather its {col, val} pairs into the panel, zero the pad entry
-__global__ void __launch_bounds__(256) build_panel_kernel(const SegDesc *seg, int n_seg, const int *idx,
+// one warp per segment: gather its {col * k4, val} pairs into the panel, nop entries in the padding
+__global__ void __launch_bounds__(256) build_panel_kernel(const SegDesc *seg, int n_seg, int k4, int pad, const int *idx,
                                                           const float *val, int2 *panel) {
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= n_seg) return;
     const SegDesc d = seg[gw];
-    const int padded = (d.len + 1) & ~1;
+    const int padded = (d.len + pad - 1) / pad * pad;
     for (int t = lane; t < padded; t += 32) {
-        int2 e = make_int2(0, 0);
-        if (t < d.len) e = make_int2(idx[d.nnz_begin + t], __float_as_int(val[d.nnz_begin + t]));
+        int2 e = make_int2(-1, 0);
+        if (t < d.len) e = make_int2(idx[d.nnz_begin + t] * k4, __float_as_int(val[d.nnz_begin + t]));
         panel[(size_t)d.panel_off + t] = e;
     }
 }
@@ -651,21 +646,21 @@ int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_b
     return 0;
 }
 
-int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, const int *d_idx, const float *d_val,
+int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, int k4, const int *d_idx, const float *d_val,
                         int2 *d_lpanel, cudaStream_t stream) {
     if (n_light == 0) return 0;
     const long long threads = (long long)n_light * 32;
-    build_lpanel_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_light_desc, n_light, groups, d_idx,
+    build_lpanel_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_light_desc, n_light, groups, k4, d_idx,
                                                                               d_val, d_lpanel);
     SB_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_build_panel(const SegDesc *d_seg, int n_seg, const int *d_idx, const float *d_val,
+int launch_build_panel(const SegDesc *d_seg, int n_seg, int k4, int pad, const int *d_idx, const float *d_val,
                        int2 *d_panel, cudaStream_t stream) {
     if (n_seg == 0) return 0;
     const long long threads = (long long)n_seg * 32;
-    build_panel_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_seg, n_seg, d_idx, d_val,
+    build_panel_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_seg, n_seg, k4, pad, d_idx, d_val,
                                                                              d_panel);
     SB_CUDA(cudaGetLastError());
     return 0;

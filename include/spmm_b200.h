@@ -133,7 +133,9 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *   1 heavy_rows int32[n_heavy]     heavy rows in processing order
  *   2 heavy_seg0 int32[n_heavy+1]   first segment of each heavy row (prefix)
  *   3 seg_desc   int32[n_seg*4]     {row, panel_off, len, nnz_begin} per segment
- *   4 panel      int32[panel_len*2] {col, float bits of val} pairs, segment-major
+ *   4 panel      int32[panel_len*2] {col * feat_in/4, float bits of val} pairs, segment-major (the column is stored as
+ *                                   the B row's offset in float4 units, so a gather address is one multiply-add);
+ *                                   each segment is padded with nops {-1, 0} to a multiple of 4 * (32 / lanes) entries
  *   5 light_desc int32[n_light*4]   {row, first CSR position, nonzeros, slot of its header in lpanel} per light
  *                                   row, same order as row_perm
  *   8 ltask      int32[n_ltask*2]   {lpanel offset, steps per lane group} per light-stream task
@@ -141,8 +143,8 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *                                   ltask, a heavy segment as {-1 - segment, 0}. Bucketed rows: segments first, then the
  *                                   light tasks; natural order: merged by the row each task starts with
  *   9 lpanel     int32[lpanel_len*2] light rows as a stream of {x, y} entries: header {0x80000000|row, 0},
- *                                   nonzero {col, float bits of val}, nop {-1, -1}; within a task, entry j of
- *                                   lane group g sits at offset + j*groups + g
+ *                                   nonzero {col * feat_in/4, float bits of val}, nop {-1, -1}; within a task, entry j
+ *                                   of lane group g sits at offset + j*groups + g; tasks are padded to 4-step multiples
  *   6 seg_hrow   int32[n_seg]       index into heavy_rows of each segment's row
  *   7 split      int32[(n_col_blocks+1)*num_v]  block-major: CSR position where column block b starts
  *                                   in row r (empty when n_col_blocks == 1)

@@ -87,8 +87,11 @@ def split_rows(ptr, idx, nb: int, b_rows: int) -> np.ndarray:
     return out.astype(np.int32)
 
 
-def plan(ptr, idx, val, seg_len: int, reorder: bool = True, rb=None, re=None, skip_empty: bool = False) -> dict:
-    """Plan of the whole matrix (rb/re omitted) or of one column block (row r owns [rb[r], re[r]))."""
+def plan(ptr, idx, val, seg_len: int, reorder: bool = True, rb=None, re=None, skip_empty: bool = False, k4: int = 1,
+         pad: int = 2) -> dict:
+    """Plan of the whole matrix (rb/re omitted) or of one column block (row r owns [rb[r], re[r])).
+    k4 = feat // 4: panels store a column as the B row's offset in float4 units (col * k4).
+    pad = 4 * (32 // lanes): every segment's span is padded with nop entries (-1, 0) to a multiple of it."""
     ptr = np.asarray(ptr, np.int64)
     m = len(ptr) - 1
     rb = ptr[:-1] if rb is None else np.asarray(rb, np.int64)
@@ -112,11 +115,12 @@ def plan(ptr, idx, val, seg_len: int, reorder: bool = True, rb=None, re=None, sk
             b = begin + j * d // nseg
             e = begin + (j + 1) * d // nseg
             seg_desc.append((int(r), off, e - b, b))
-            cols = np.asarray(idx[b:e], np.int32)
+            cols = (np.asarray(idx[b:e], np.int64) * k4).astype(np.int32)
             bits = np.asarray(val[b:e], np.float32).view(np.int32)
             pairs = np.stack([cols, bits], axis=1)
-            if (e - b) & 1:
-                pairs = np.concatenate([pairs, np.zeros((1, 2), np.int32)])
+            extra = -(e - b) % pad
+            if extra:
+                pairs = np.concatenate([pairs, np.tile(np.asarray([[-1, 0]], np.int32), (extra, 1))])
             panel.append(pairs)
             off += len(pairs)
         heavy_seg0.append(len(seg_desc))
@@ -169,9 +173,7 @@ def pack_light(cost, groups: int, steps: int):
 
     def close():
         nonlocal off, fill
-        mx = max(fill)
-        if groups == 1 and mx % 2:
-            mx += 1
+        mx = (max(fill) + 3) // 4 * 4
         tasks.append((off, mx))
         off += mx * groups
         fill = [0] * groups
@@ -188,7 +190,7 @@ def pack_light(cost, groups: int, steps: int):
     return np.asarray(dst, np.int32), np.asarray(tasks, np.int32).reshape(-1, 2), off
 
 
-def light_stream(plan_dict, idx, val, groups: int, steps: int) -> dict:
+def light_stream(plan_dict, idx, val, groups: int, steps: int, k4: int = 1) -> dict:
     """light_desc with header slots, task list and the stream panel for a plan() result."""
     ld = plan_dict["light_desc"].copy()
     dst, tasks, length = pack_light(ld[:, 2].astype(np.int64) + 1, groups, steps)
@@ -200,7 +202,7 @@ def light_stream(plan_dict, idx, val, groups: int, steps: int) -> dict:
         panel[d] = (np.uint32(0x80000000 | int(row)).astype(np.int32), 0)   # header
         if deg:
             sl = d + (1 + np.arange(deg)) * groups
-            panel[sl, 0] = idx[begin:begin + deg]
+            panel[sl, 0] = idx[begin:begin + deg].astype(np.int64) * k4
             panel[sl, 1] = bits[begin:begin + deg]
     return {"light_desc": ld, "ltask": tasks, "lpanel": panel}
 

@@ -364,11 +364,11 @@ def test_plan_matches_oracle(shape, seg_len, reorder):
     op = H.SpMMB200(g, 32, seg_len=seg_len, reorder=reorder)
     op.preprocess(vin, vout)
     info = op.plan_info()
-    want = P.plan(ptr, idx, g.val.cpu().numpy(), info["seg_len"], bool(reorder))
+    want = P.plan(ptr, idx, g.val.cpu().numpy(), info["seg_len"], bool(reorder), k4=8, pad=4 * (32 // info["lanes"]))
     got = op.plan_arrays()
     assert info["seg_len"] == (seg_len or P.auto_seg_len(len(idx), 32))
     assert info["kslice"] == P.auto_kslice(g.num_v, 32)
-    want.update(P.light_stream(want, idx, g.val.cpu().numpy(), 32 // info["lanes"], info["light_steps"]))
+    want.update(P.light_stream(want, idx, g.val.cpu().numpy(), 32 // info["lanes"], info["light_steps"], k4=8))
     want["utask"] = P.unified_tasks(want, want, bool(reorder))
     assert np.array_equal(got["utask"], want["utask"]) and info["n_utask"] == info["n_ltask"] + info["n_seg"]
     total = int(want["light_desc"][:, 2].astype(np.int64).sum()) + len(want["light_desc"])
@@ -400,8 +400,9 @@ def test_column_block_plan_matches_oracle(shape, K, nb, seg_len):
         inf = op.plan_info(b)
         assert (inf["col_begin"], inf["col_end"]) == (b * cpb, min(M, (b + 1) * cpb))
         assert np.array_equal(got["split"], split)
-        want = P.plan(ptr, idx, val, inf["seg_len"], True, rb=split[b], re=split[b + 1], skip_empty=b > 0)
-        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"]))
+        want = P.plan(ptr, idx, val, inf["seg_len"], True, rb=split[b], re=split[b + 1], skip_empty=b > 0, k4=K // 4,
+                      pad=4 * (32 // inf["lanes"]))
+        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"], k4=K // 4))
         for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
             assert np.array_equal(got[k], want[k]), (b, k)
         # every nonzero of the block lies in its band of B rows

@@ -124,7 +124,7 @@ def test_plan_host_matches_oracle():
         ptr, idx = H.gen_named_graph(name)
         val = np.zeros(len(idx), np.float32)
         got = H.plan_host(ptr, 256, sl, ro)
-        want = P.plan(ptr, idx, val, sl or P.auto_seg_len(len(idx), 256), ro)
+        want = P.plan(ptr, idx, val, sl or P.auto_seg_len(len(idx), 256), ro, pad=4)      # K=256: one lane group
         for k in ("row_perm", "heavy_rows", "heavy_seg0", "seg_desc"):
             assert np.array_equal(got[k], want[k]), (name, k)
         assert got["panel_len"] == len(want["panel"])
@@ -133,9 +133,9 @@ def test_plan_host_matches_oracle():
     ptr, idx = H.gen_named_graph("arxiv")
     assert P.auto_seg_len(len(idx), 256) == 256 and P.auto_seg_len(len(idx), 32) == 128 and P.auto_seg_len(1, 128) == 256
     assert P.auto_seg_len(len(idx), 100) == 256 and P.auto_seg_len(len(idx), 64) == 128
-    a, b = H.plan_host(ptr, 32), P.plan(ptr, idx, np.zeros(len(idx), np.float32), 128, True)
+    a, b = H.plan_host(ptr, 32), P.plan(ptr, idx, np.zeros(len(idx), np.float32), 128, True, pad=16)   # K=32: 4 groups
     assert np.array_equal(a["seg_desc"], b["seg_desc"]) and np.array_equal(a["row_perm"], b["row_perm"])
-    a, b = H.plan_host(ptr, 256), P.plan(ptr, idx, np.zeros(len(idx), np.float32), 256, True)
+    a, b = H.plan_host(ptr, 256), P.plan(ptr, idx, np.zeros(len(idx), np.float32), 256, True, pad=4)
     assert np.array_equal(a["seg_desc"], b["seg_desc"]) and np.array_equal(a["row_perm"], b["row_perm"])
     assert len(H.plan_host(ptr, 30)["heavy_rows"]) == 0       # scalar path keeps every row whole
     # cross-check with the student's task split (spmm_opt.cu:43-54): same number of pieces per row at 256
@@ -168,7 +168,7 @@ def test_pack_light_host_matches_oracle():
                 # slots of different rows never collide, tasks tile the panel, offsets stay 16-byte aligned
                 used = np.concatenate([d + np.arange(c) * groups for d, c in zip(dst, cost)])
                 assert len(np.unique(used)) == len(used) and used.max() < length
-                assert np.all(ltask[:, 0] % 2 == 0) and np.all((ltask[:, 1] * groups) % 2 == 0)
+                assert np.all(ltask[:, 0] % 4 == 0) and np.all(ltask[:, 1] % 4 == 0)
                 assert np.array_equal(ltask[1:, 0], (ltask[:, 0] + ltask[:, 1] * groups)[:-1])
 
 
@@ -184,7 +184,7 @@ def test_property_based_plan_and_packing():
         idx = np.zeros(nnz, np.int32)
         val = np.zeros(nnz, np.float32)
         got = H.plan_host(ptr, 32, seg_len, reorder)
-        want = P.plan(ptr, idx, val, seg_len, reorder)
+        want = P.plan(ptr, idx, val, seg_len, reorder, pad=16)       # feat 32 -> 8 lanes -> 4 groups -> pad 16
         for k in ("row_perm", "heavy_rows", "heavy_seg0", "seg_desc"):
             assert np.array_equal(got[k], want[k]), k
         # every row appears exactly once; segments tile their rows

@@ -95,6 +95,7 @@ def bench(name, K, optlist, iters=10):
 
 print(torch.cuda.get_device_name(0), flush=True)
 if mode in ("quick", "full"):
-    parity("arxiv", 256, reorder=0)
-    for g, K in (("products", 256), ("reddit", 256), ("citation", 256), ("amazon_cogdl", 256), ("arxiv", 256), ("arxiv", 32)):
-        bench(g, K, [{}, {"reorder": 1}, {"reorder": 0}], iters=10 if g == "arxiv" else 5)
+    parity("c0", 32)
+    parity("arxiv", 256)
+    for g, K in (("arxiv", 32), ("arxiv", 256), ("collab", 32), ("youtube", 32), ("reddit", 32), ("reddit", 64), ("reddit", 128), ("reddit", 256), ("products", 256), ("products", 32)):
+        bench(g, K, [{}], iters=10 if g in ("arxiv", "collab", "youtube") else 5)
