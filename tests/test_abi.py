@@ -79,3 +79,19 @@ def test_cpp_adapter_compiles_standalone_and_against_the_handout(tmp_path):
     if os.path.isdir(hand):
         r = subprocess.run(base + ["-DSPMM_B200_WITH_HANDOUT", "-I", hand, str(tu)], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_example_builds(tmp_path):
+    """examples/minimal.c: the boundary used from C99 with only the CUDA runtime API (link check; it runs on the GPU box
+    in tests/test_gpu_parity.py)."""
+    import subprocess
+    cuda = "/usr/local/cuda"
+    if not os.path.isdir(os.path.join(cuda, "include")):
+        import pytest
+        pytest.skip("no CUDA toolkit headers")
+    exe = str(tmp_path / "minimal")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(ROOT, "examples", "minimal.c"), "-L", os.path.join(ROOT, "hpc_b200"), "-lspmm_b200",
+                        "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "hpc_b200"), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

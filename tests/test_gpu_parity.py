@@ -702,3 +702,19 @@ def test_fuzz_random_graphs_and_options():
             raise AssertionError(f"fuzz case {case}: m={m} nnz={len(idx)} K={K} opts={opts}: {e}")
         finally:
             op.close()
+
+
+def test_plain_c_example_runs(tmp_path):
+    """examples/minimal.c end to end: plain C host, CUDA runtime API, the C ABI — prints and checks a 3x3 product."""
+    import subprocess
+    from conftest import ROOT
+    cuda = "/usr/local/cuda"
+    exe = str(tmp_path / "minimal")
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(ROOT, "examples", "minimal.c"), "-L", os.path.join(ROOT, "hpc_b200"), "-lspmm_b200",
+                        "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "hpc_b200"), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split() == ["32", "37", "42", "47", "0", "0", "0", "0", "-0", "-1", "-2", "-3"]
