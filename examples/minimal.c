@@ -39,6 +39,6 @@ int main(void) {
     cudaMemcpy(c, d_c, sizeof c, cudaMemcpyDeviceToHost);
     for (i = 0; i < 3; ++i) printf("%g %g %g %g\n", c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
     CK(spmm_b200_destroy(h));
-    /* expected: 32 37 42 47 / 0 0 0 0 / -0 -1 -2 -3 */
+    /* expected: 32 37 42 47 / 0 0 0 0 / 0 -1 -2 -3 */
     return !(c[0] == 32.f && c[3] == 47.f && c[4] == 0.f && c[9] == -1.f && c[11] == -3.f);
 }

@@ -717,4 +717,4 @@ def test_plain_c_example_runs(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.split() == ["32", "37", "42", "47", "0", "0", "0", "0", "-0", "-1", "-2", "-3"]
+    assert [float(x) for x in r.stdout.split()] == [32, 37, 42, 47, 0, 0, 0, 0, 0, -1, -2, -3]
