@@ -181,13 +181,13 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 t
         const int s = k % kStages;
         mbar_wait(&bars[s], (uint32_t)(k / kStages) & 1u);
         const int n = min(kChunk, len - k * kChunk);
-        const int2 *e = buf + s * kChunk;
-        for (int t0 = 0; t0 < n; t0 += GROUPS * U) {
+        const int2 *ep = buf + s * kChunk + g;   // this lane group's entries: ep[0], ep[GROUPS], ...
+        for (int t0 = 0; t0 < n; t0 += GROUPS * U, ep += GROUPS * U) {
             float4 b[U][VEC];
             int2 cv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                cv[u] = e[t0 + u * GROUPS + g];   // in range: a task is padded to a multiple of 4 steps
+                cv[u] = ep[u * GROUPS];   // in range: a task is padded to a multiple of 4 steps
                 if (cv[u].x >= 0) {
                     const float4 *brow = bbase + (unsigned)cv[u].x;
 #pragma unroll
