@@ -9,3 +9,4 @@ from .graph import (  # noqa: F401
     GRAPH_SHAPES, RUN_ALL_DATASETS, gen_degrees, gen_graph, gen_named_graph, load_graph, partition_rows, rebase_ptr, set_host_threads,
     write_graph,
 )
+from .mg import MultiGpuSpMM  # noqa: F401

@@ -41,6 +41,7 @@ SIGNATURES = {
     "spmm_b200_set_option": (_I, [_P, C.c_char_p, _LL]),
     "spmm_b200_set_gather": (_I, [_P, _I, C.POINTER(_P), _P, _LL]),
     "spmm_b200_preprocess": (_I, [_P, _P, _P, _P]),
+    "spmm_b200_refresh_values": (_I, [_P, _P]),
     "spmm_b200_run": (_I, [_P, _P, _P, _P]),
     "spmm_b200_run_profiled": (_I, [_P, _P, _P, _P, C.POINTER(C.c_float)]),
     "spmm_b200_destroy": (_I, [_P]),
@@ -62,6 +63,20 @@ SIGNATURES = {
     "spmm_b200_write_graph": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _I]),
     "spmm_b200_partition_rows": (_I, [_P, _I, _I, _P]),
     "spmm_b200_rebase_ptr": (_I, [_P, _I, _I, _P]),
+    "spmm_b200_set_replicate": (_I, [_P, _I, _I, C.POINTER(_P), _P, C.POINTER(_P)]),
+    "spmm_b200_run_host_sharded": (_I, [_P, _P, _I, _I, _P, _P]),
+    "spmm_b200_mg_create": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, C.POINTER(_P)]),
+    "spmm_b200_mg_set_option": (_I, [_P, C.c_char_p, _LL]),
+    "spmm_b200_mg_preprocess": (_I, [_P]),
+    "spmm_b200_mg_info": (_I, [_P, C.POINTER(_I), _P, C.POINTER(_I)]),
+    "spmm_b200_mg_device_buffers": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "spmm_b200_mg_run_host": (_I, [_P, _P, _P]),
+    "spmm_b200_mg_run": (_I, [_P]),
+    "spmm_b200_mg_sync": (_I, [_P]),
+    "spmm_b200_mg_set_fused": (_I, [_P, _I]),
+    "spmm_b200_mg_allgather": (_I, [_P]),
+    "spmm_b200_mg_swap": (_I, [_P]),
+    "spmm_b200_mg_destroy": (_I, [_P]),
 }
 
 

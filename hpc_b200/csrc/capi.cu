@@ -59,6 +59,11 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in) {
         set_error("spmm_b200_set_feat: bad arguments");
         return SPMM_B200_EINVAL;
     }
+    if (h->n_gather > 0 && feat_in % 4 != 0) {
+        // the scalar fallback kernel has no stacked-layer epilogue: refuse rather than drop it silently
+        set_error("spmm_b200_set_feat: the gather epilogue is on and needs feat_in %% 4 == 0 (switch it off first)");
+        return SPMM_B200_EINVAL;
+    }
     h->feat = feat_in;
     free_plan(h->plan);
     return 0;
@@ -77,7 +82,9 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     else if (!strcmp(name, "light_steps") && value >= 0 && value <= 65536) h->opt_light_steps = value;
     else if (!strcmp(name, "col_blocks") && value >= 0 && value <= 64) h->opt_col_blocks = value;
     else if (!strcmp(name, "b_rows") && value >= 0 && value <= 0x7fffffffll) {
-        h->b_rows = (int)value;   // does not touch the plan
+        // the plan depends on it (column bounds check, 32-bit offset guard, column-block bands)
+        if ((int)value != h->b_rows) h->plan.ready = false;
+        h->b_rows = (int)value;
         return 0;
     }
     else {
@@ -121,40 +128,63 @@ int spmm_b200_preprocess(spmm_b200_t h, const float *vin, float *vout, void *str
     return build_plan(h, (cudaStream_t)stream);
 }
 
-int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream) {
+// argument checks shared by run and run_profiled
+static int check_run_args(const char *who, spmm_b200_t h, const float *vin, const float *vout) {
     if (!h) {
-        set_error("spmm_b200_run: null handle");
+        set_error("%s: null handle", who);
         return SPMM_B200_EINVAL;
     }
     if (!h->plan.ready) {
-        set_error("spmm_b200_run: preprocess has not been called");
+        set_error("%s: preprocess has not been called", who);
         return SPMM_B200_ESTATE;
     }
     if ((size_t)h->num_v * h->feat > 0 && (!vin || !vout)) {
-        set_error("spmm_b200_run: null vin/vout");
+        set_error("%s: null vin/vout", who);
         return SPMM_B200_EINVAL;
     }
     if (!h->plan.scalar && (((uintptr_t)vin | (uintptr_t)vout) & 15)) {
-        set_error("spmm_b200_run: vin/vout must be 16-byte aligned");
+        set_error("%s: vin/vout must be 16-byte aligned", who);
         return SPMM_B200_EINVAL;
     }
+    return 0;
+}
+
+int spmm_b200_refresh_values(spmm_b200_t h, void *stream) {
+    if (!h) {
+        set_error("spmm_b200_refresh_values: null handle");
+        return SPMM_B200_EINVAL;
+    }
+    if (!h->plan.ready) {
+        set_error("spmm_b200_refresh_values: preprocess has not been called");
+        return SPMM_B200_ESTATE;
+    }
+    return refresh_panels(h, (cudaStream_t)stream);
+}
+
+int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream) {
+    int rc = check_run_args("spmm_b200_run", h, vin, vout);
+    if (rc) return rc;
     return launch_spmm(h, vin, vout, (cudaStream_t)stream, &h->plan.launches);
 }
 
 int spmm_b200_run_profiled(spmm_b200_t h, const float *vin, float *vout, void *stream, float *ms) {
-    if (!h || !ms) {
+    if (!ms) {
         set_error("spmm_b200_run_profiled: null argument");
         return SPMM_B200_EINVAL;
     }
-    if (!h->plan.ready) {
-        set_error("spmm_b200_run_profiled: preprocess has not been called");
-        return SPMM_B200_ESTATE;
+    int rc = check_run_args("spmm_b200_run_profiled", h, vin, vout);
+    if (rc) return rc;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t ce = cudaEventCreate(&ev[i]);
+        if (ce != cudaSuccess) {
+            if (i == 1) cudaEventDestroy(ev[0]);
+            SB_CUDA(ce);
+        }
     }
-    cudaEvent_t ev[2];
-    for (int i = 0; i < 2; ++i) SB_CUDA(cudaEventCreate(&ev[i]));
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaEventRecord(ev[0], s);
-    int rc = launch_spmm(h, vin, vout, s, &h->plan.launches);
+    rc = launch_spmm(h, vin, vout, s, &h->plan.launches);
     if (e == cudaSuccess) e = cudaEventRecord(ev[1], s);
     if (e == cudaSuccess) e = cudaEventSynchronize(ev[1]);
     if (rc == 0 && e == cudaSuccess) e = cudaEventElapsedTime(ms, ev[0], ev[1]);

@@ -25,7 +25,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 constexpr int kMaxGather = 16;
 
 // One heavy-row segment: `len` nonzeros of `row` starting at CSR position `nnz_begin`,
-// staged at panel[panel_off .. panel_off + roundup2(len)).
+// staged at panel[panel_off .. panel_off + len rounded up to whole gather batches, 4 * (32 / lanes) entries).
 struct SegDesc {
     int row;
     int panel_off;
@@ -119,6 +119,12 @@ struct spmm_b200_handle {
     float *gather_mc = nullptr;
     long long gather_row0 = 0;
     int b_rows = 0;   // rows of B (0 = num_v); > num_v for a row partition of a larger graph
+    // sharded host I/O over NVLink (replicate.cu): every rank's copy of B and flag words, as mapped in this process
+    int rep_world = 0, rep_rank = 0;
+    float *rep_b[spmm_b200::kMaxGather] = {nullptr};
+    float *rep_mc = nullptr;
+    unsigned int *rep_flags[spmm_b200::kMaxGather] = {nullptr};
+    unsigned int rep_epoch = 0;
 };
 
 namespace spmm_b200 {
@@ -126,6 +132,7 @@ namespace spmm_b200 {
 // preprocess.cu
 int build_plan(spmm_b200_handle *h, cudaStream_t stream);
 void free_plan(Plan &p);
+int refresh_panels(spmm_b200_handle *h, cudaStream_t stream);
 
 // spmm_kernels.cu
 // band_ready: NULL, or one event per column block that the stream waits on before that block's pass
@@ -144,6 +151,15 @@ int launch_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream
                        float stddev, cudaStream_t stream);
 int launch_valid(const float *d_y, const float *d_y2, long long num, unsigned long long *d_count,
                  cudaStream_t stream);
+
+// replicate.cu
+// Push `count` floats at src (16-byte aligned, count % 4 == 0) to the same offset `off` of every buffer in targets[0..n)
+// except targets[skip] (skip < 0: none) — or, when mc is non-NULL, once through that NVLS multicast address.
+int launch_push_rows(const float *src, long long off, long long count, int n, float *const *targets, int skip, float *mc,
+                     cudaStream_t stream);
+// Cross-rank barrier on `stream`: phase-th flag word of this rank is set to `epoch` in every rank's flag array, then the
+// kernel waits until every rank's word in the local array has reached `epoch`. flags[r] = uint32[2 * world] of rank r.
+int launch_xrank_barrier(unsigned int *const *flags, int world, int rank, int phase, unsigned int epoch, cudaStream_t stream);
 
 // Packs light rows (costs = deg + 1 entries each, in plan order) into stream tasks of `groups` interleaved lane-group
 // lanes with about `steps` entries each; dst[i] = lpanel slot of row i's header. Returns the lpanel length.

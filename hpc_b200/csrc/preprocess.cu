@@ -18,14 +18,29 @@
 //               entries, packed into equal-sized warp tasks by pack_light_host (rule stated there)
 //   column blocks: when B exceeds the L2 (auto_col_blocks), every row is split at the band boundaries
 //               (split[b][r]) and the whole plan above is built once per block over [split[b][r], split[b+1][r])
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "common.h"
 
 namespace spmm_b200 {
+
+// SPMM_B200_PREP_TRACE=1: per-phase wall times of preprocess on stderr (tools/prep_probe.py)
+struct PrepTrace {
+    bool on = getenv("SPMM_B200_PREP_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[prep] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 void free_plan(Plan &p) {
     for (BlockPlan &b : p.blocks) {
@@ -217,6 +232,7 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
                        cudaStream_t stream) {
     Plan &p = h->plan;
     const int M = h->num_v, K = h->feat;
+    PrepTrace tr;
     std::vector<int> row_perm, heavy_rows, heavy_seg0;
     std::vector<SegDesc> segs;
     long long panel_len = 0;
@@ -236,6 +252,7 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
     int rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, pad, row_perm, heavy_rows, heavy_seg0,
                             segs, &panel_len);
     if (rc) return rc;
+    tr.lap("block: plan_rows_host");
     bp.n_light = (int)row_perm.size();
     bp.n_heavy = (int)heavy_rows.size();
     bp.n_seg = (int)segs.size();
@@ -268,6 +285,7 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
             return SPMM_B200_EINVAL;
         }
     }
+    tr.lap("block: pack_light_host");
     for (int i = 0; i < bp.n_light; ++i) {
         const int r = row_perm[i];
         light[i] = make_int4(r, rb[r], re[r] - rb[r], p.scalar ? 0 : dst[i]);
@@ -303,6 +321,7 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
         for (const int2 &t : ltasks) utask.push_back(t);
     }
     bp.n_utask = (int)utask.size();
+    tr.lap("block: light_desc + utask");
     std::vector<int> seg_hrow((size_t)bp.n_seg);
     for (int hr = 0; hr < bp.n_heavy; ++hr)
         for (int sgm = heavy_seg0[hr]; sgm < heavy_seg0[hr + 1]; ++sgm) seg_hrow[sgm] = hr;
@@ -329,6 +348,7 @@ static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const 
         if ((rc = launch_build_panel(bp.d_seg_desc, bp.n_seg, K / 4, pad, h->d_idx, h->d_val, bp.d_panel, stream))) return rc;
     }
     SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+    tr.lap("block: upload + panels");
     return 0;
 }
 
@@ -338,6 +358,14 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     h->plan_select = 0;
     const int M = h->num_v, K = h->feat;
     const int b_rows = h->b_rows > 0 ? h->b_rows : M;
+    if (K == 0 || M == 0) {
+        // nothing to compute (launch_spmm returns before touching the plan): an empty, ready plan of one empty block
+        p.block = (int)h->opt_block;
+        p.n_col_blocks = 1;
+        p.blocks.resize(1);
+        p.ready = true;
+        return 0;
+    }
     p.block = (int)h->opt_block;
     p.scalar = (K % 4) != 0;
     p.kslice = h->opt_kslice > 0 ? (int)h->opt_kslice : auto_kslice(M, K);
@@ -359,6 +387,7 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     if (p.scalar || M == 0 || nb < 1) nb = 1;
     if (nb > b_rows) nb = b_rows > 0 ? b_rows : 1;
 
+    PrepTrace tr;
     std::vector<int> ptr((size_t)M + 1, 0);
     if (M > 0) {
         SB_CUDA(cudaMemcpyAsync(ptr.data(), h->d_ptr, sizeof(int) * ((size_t)M + 1), cudaMemcpyDeviceToHost,
@@ -369,7 +398,13 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         set_error("CSR ptr is inconsistent: ptr[0]=%d ptr[num_v]=%d num_e=%d", ptr[0], ptr[M], h->num_e);
         return SPMM_B200_EINVAL;
     }
+    for (int r = 0; r < M; ++r)   // whatever the row order: a negative degree would turn into out-of-bounds panel slots
+        if (ptr[r + 1] < ptr[r]) {
+            set_error("CSR ptr decreases at row %d", r);
+            return SPMM_B200_EINVAL;
+        }
 
+    tr.lap("ptr D2H + checks");
     {   // columns must address rows of B
         int *d_bad = nullptr, bad = 0;
         SB_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
@@ -386,10 +421,12 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         }
     }
 
+    tr.lap("check_cols");
     // split every row at the column-block boundaries (needs ascending columns inside a row; a graph
     // that is not sorted falls back to a single block)
     std::vector<int> split;
-    const int cols_per_block = nb > 1 ? (b_rows + nb - 1) / nb : b_rows;
+    int cols_per_block = nb > 1 ? (b_rows + nb - 1) / nb : b_rows;
+    if (nb > 1) nb = (b_rows + cols_per_block - 1) / cols_per_block;   // every band starts inside B (b_rows = 10, 7 bands -> 5 of 2 rows)
     if (nb > 1) {
         int *d_unsorted = nullptr;
         SB_CUDA(cudaMalloc((void **)&p.d_split, sizeof(int) * (size_t)(nb + 1) * M));
@@ -412,6 +449,7 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
             SB_CUDA(cudaMemcpy(split.data(), p.d_split, sizeof(int) * split.size(), cudaMemcpyDeviceToHost));
         }
     }
+    tr.lap("split_rows + D2H");
     p.n_col_blocks = nb;
     p.blocks.resize(nb);
     for (int b = 0; b < nb; ++b) {
@@ -427,6 +465,23 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         if (rc) return rc;
     }
     p.ready = true;
+    return 0;
+}
+
+// Re-stage the {col, val} panels from the caller's idx/val (asynchronous on `stream`): the plan's structure
+// (row order, segments, tasks, slots) depends on ptr only, so new edge values need no new plan.
+int refresh_panels(spmm_b200_handle *h, cudaStream_t stream) {
+    Plan &p = h->plan;
+    if (p.scalar || h->feat == 0 || h->num_v == 0) return 0;   // the scalar kernel reads idx/val at run time
+    const int groups = 32 / p.lanes, pad = 4 * groups, k4 = h->feat / 4;
+    for (BlockPlan &bp : p.blocks) {
+        int rc;
+        if (bp.n_ltask > 0 &&
+            (rc = launch_build_lpanel(bp.d_light_desc, bp.n_light, groups, k4, h->d_idx, h->d_val, bp.d_lpanel, stream)))
+            return rc;
+        if (bp.n_seg > 0 && (rc = launch_build_panel(bp.d_seg_desc, bp.n_seg, k4, pad, h->d_idx, h->d_val, bp.d_panel, stream)))
+            return rc;
+    }
     return 0;
 }
 

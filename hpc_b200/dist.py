@@ -39,9 +39,14 @@ class RowPartition:
 
 def _default_op_factory(local_ptr, local_idx, local_val, feat, b_rows, device, options):
     from .spmm import CSR, SpMMB200
+    if isinstance(local_val, torch.Tensor):
+        d_val = local_val.to(device)
+        if d_val.untyped_storage().nbytes() > d_val.numel() * d_val.element_size():
+            d_val = d_val.clone()   # a slice of the whole graph's values: keep only this block alive
+    else:
+        d_val = torch.from_numpy(np.ascontiguousarray(local_val)).to(device)
     g = CSR(len(local_ptr) - 1, len(local_idx),
-            torch.from_numpy(local_ptr).to(device), torch.from_numpy(np.ascontiguousarray(local_idx)).to(device),
-            local_val.to(device) if isinstance(local_val, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local_val)).to(device))
+            torch.from_numpy(local_ptr).to(device), torch.from_numpy(np.ascontiguousarray(local_idx)).to(device), d_val)
     return SpMMB200(g, feat, b_rows=b_rows, **options)
 
 
@@ -79,26 +84,19 @@ class ShardedSpMM:
             full[: elems[0]].copy_(vout_local[: elems[0]])
             return full
         backend = dist.get_backend(self.group)
+        views = [full[offs[g]: offs[g + 1]] for g in range(self.world)]
         if backend == "nccl":
-            # one NCCL all-gather of equal (padded) blocks into a staging buffer, then one
-            # device-side compaction per peer block
-            mx = max(elems)
-            if getattr(self, "_stage", None) is None or self._stage.numel() < mx * self.world:
-                self._stage = torch.empty(mx * self.world, dtype=full.dtype, device=full.device)
-                self._pad = torch.zeros(mx, dtype=full.dtype, device=full.device)
-            self._pad[: elems[self.rank]].copy_(vout_local[: elems[self.rank]])
-            dist.all_gather_into_tensor(self._stage, self._pad, group=self.group)
-            for g in range(self.world):
-                full[offs[g]: offs[g + 1]].copy_(self._stage[g * mx: g * mx + elems[g]])
+            # all-gather-v straight into place: with unequal block sizes ProcessGroupNCCL issues one coalesced group of
+            # ncclBroadcast calls (root g -> views[g]); no padding, no staging buffer, no compaction copies
+            dist.all_gather(views, vout_local[: elems[self.rank]], group=self.group)
         else:
             # gloo (CPU tests): one broadcast per block, straight into place
             works = []
             for g in range(self.world):
-                view = full[offs[g]: offs[g + 1]]
                 if g == self.rank:
-                    view.copy_(vout_local[: elems[g]])
+                    views[g].copy_(vout_local[: elems[g]])
                 if elems[g]:
-                    works.append(dist.broadcast(view, src=dist.get_global_rank(self.group, g) if self.group else g,
+                    works.append(dist.broadcast(views[g], src=dist.get_global_rank(self.group, g) if self.group else g,
                                                 group=self.group, async_op=True))
             for w in works:
                 w.wait()
@@ -137,6 +135,35 @@ class ShardedSpMM:
         self.op.run(vin, vout_local)
         self._sym_hdls[buffer].barrier()
         return self._sym_bufs[buffer]
+
+    # ---- sharded host I/O: B replicated over NVLink instead of N uploads over PCIe ------------------------------
+
+    def enable_sharded_host_io(self, use_multicast: bool = True) -> torch.Tensor:
+        """Allocates this rank's full copy of B and the barrier flag words as symmetric memory (torch's
+        `_symmetric_memory`: allocation + address exchange only) and hands every rank's mapping to the operator
+        (spmm_b200_set_replicate). Rank g then uploads rows [g*num_v/world, (g+1)*num_v/world) of B."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group or dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._rep_b = symm_mem.empty(self.num_v * self.feat, dtype=torch.float32, device=dev)
+        self._rep_flags = symm_mem.empty(max(64, 2 * self.world), dtype=torch.int32, device=dev)
+        self._rep_flags.zero_()
+        hb = symm_mem.rendezvous(self._rep_b, group)
+        hf = symm_mem.rendezvous(self._rep_flags, group)
+        torch.cuda.synchronize()
+        dist.barrier(group)   # every rank's flags are zero before anybody signals
+        mc = (hb.multicast_ptr or 0) if use_multicast else 0
+        self._rep_handles = (hb, hf)
+        self.rep_multicast = bool(mc)
+        self.op.set_replicate(self.world, self.rank, hb.buffer_ptrs, mc, hf.buffer_ptrs)
+        self.up_begin = self.num_v * self.rank // self.world
+        self.up_rows = self.num_v * (self.rank + 1) // self.world - self.up_begin
+        return self._rep_b
+
+    def run_host_sharded(self, h_vin_rows: torch.Tensor, h_vout_local: torch.Tensor) -> None:
+        """h_vin_rows: this rank's rows [up_begin, up_begin + up_rows) of B on the host; h_vout_local: its block of
+        C. Collective: every rank calls it once per step."""
+        self.op.run_host_sharded(h_vin_rows, self.up_begin, self.up_rows, h_vout_local)
 
     def close(self):
         if hasattr(self.op, "close"):

@@ -103,6 +103,10 @@ class SpMMB200(SpMM):
         self._check_io(vin, vout)
         check(lib.spmm_b200_preprocess(self._h, _ptr(vin), _ptr(vout), _stream()))
 
+    def refresh_values(self) -> None:
+        """Re-stage the plan's copy of idx/val after the caller changed them in place (same ptr)."""
+        check(lib.spmm_b200_refresh_values(self._h, _stream()))
+
     def run(self, vin, vout) -> None:
         self._check_io(vin, vout)
         check(lib.spmm_b200_run(self._h, _ptr(vin), _ptr(vout), _stream()))
@@ -121,6 +125,22 @@ class SpMMB200(SpMM):
                 raise ValueError(f"{name}: need a contiguous host float32 tensor of >= {n} elements")
         check(lib.spmm_b200_run_host(self._h, C.c_void_p(h_vin.data_ptr()), C.c_void_p(h_vout.data_ptr()),
                                      _stream()))
+
+    def set_replicate(self, world: int, rank: int, peers_b, multicast_b: int, peers_flags) -> None:
+        """Sharded host I/O (spmm_b200_set_replicate): every rank's copy of B and flag words as mapped in this
+        process (device pointers as ints), the NVLS multicast address of the B copies or 0."""
+        pb = (C.c_void_p * max(1, world))(*[int(p) for p in peers_b])
+        pf = (C.c_void_p * max(1, world))(*[int(p) for p in peers_flags])
+        check(lib.spmm_b200_set_replicate(self._h, int(world), int(rank), pb, C.c_void_p(multicast_b or 0), pf))
+
+    def run_host_sharded(self, h_vin_rows: torch.Tensor, row_begin: int, row_count: int, h_vout: torch.Tensor) -> None:
+        """Collective over the ranks: upload this rank's rows of B, replicate them over NVLink, run, download the
+        local block of C, synchronise (spmm_b200_run_host_sharded)."""
+        for name, t, n in (("h_vin_rows", h_vin_rows, row_count * self.feat_in), ("h_vout", h_vout, self.num_v * self.feat_in)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
+                raise ValueError(f"{name}: need a contiguous host float32 tensor of >= {n} elements")
+        check(lib.spmm_b200_run_host_sharded(self._h, C.c_void_p(h_vin_rows.data_ptr()), int(row_begin), int(row_count),
+                                             C.c_void_p(h_vout.data_ptr()), _stream()))
 
     @property
     def launches_per_run(self) -> int:

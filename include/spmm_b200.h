@@ -51,9 +51,10 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "col_blocks" passes over A, each gathering from one band of B rows that fits the L2
  *               (0 = auto: 1 unless B is larger than the L2 and rows are long); needs ascending
  *               columns inside each row, otherwise falls back to 1
- *   "tune"      measured kernel variant, 0 (default) .. 3, see hpc_b200/csrc/spmm_kernels.cu
- *   "b_rows"    rows of B when A is a row block of a larger graph (0 = num_v); only
- *               spmm_b200_run_host needs it, to size its copy of B
+ *   "tune"      measured kernel variant, 0 (default) or 1, see hpc_b200/csrc/spmm_kernels.cu
+ *   "b_rows"    rows of B when A is a row block of a larger graph (0 = num_v). Part of the plan (column bounds
+ *               check, 32-bit offset guard, column-block bands, run_host's copy of B): changing it after
+ *               preprocess invalidates the plan
  * The reference's counterpart are the compile-time constants kBatchSize / kTasksPerBlock
  * (PA4/workspace/src/spmm_opt.cu:6-7). */
 int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value);
@@ -62,8 +63,17 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value);
  * PA4/workspace/src/spmm_opt.cu:37-69). Builds the plan: degree-bucketed row order, heavy-row
  * segments, staged col/val panels. vin/vout are hints only and are not written (the student's
  * preprocess zeroes vout, spmm_opt.cu:67-68; this engine's run overwrites vout instead).
- * Runs on `stream` and synchronises it before returning. */
+ * Runs on `stream` and synchronises it before returning.
+ * SNAPSHOT: for feat_in % 4 == 0 the plan stages a copy of idx/val ({col, val} panels) and run() reads only that
+ * copy — unlike the reference's SpMMOpt::run, which reads idx/val at run time (PA4/workspace/src/spmm_opt.cu:22-25).
+ * A caller that rewrites d_val (or d_idx without changing any row's length) in place afterwards must call
+ * spmm_b200_refresh_values before the next run; a change of ptr needs a new preprocess. */
 int spmm_b200_preprocess(spmm_b200_t h, const float *vin, float *vout, void *stream);
+
+/* Re-stages the plan's {col, val} panels from the caller's current d_idx / d_val (same ptr), asynchronously on
+ * `stream`: two small kernels per column block, no host work, no new plan (GNN edge re-weighting between layers).
+ * No reference counterpart (the reference reads idx/val live). */
+int spmm_b200_refresh_values(spmm_b200_t h, void *stream);
 
 /* SpMM::run(float *vin, float *vout)  (spmm_base.h:32; PA4/handout/src/spmm_ref.cu:27-30).
  * Asynchronous on `stream` (a cudaStream_t; NULL = the default stream, as in the reference).
@@ -218,6 +228,63 @@ int spmm_b200_partition_rows(const int *h_ptr, int num_v, int parts, int *bounds
 
 /* Rebase one partition: out_ptr[i] = h_ptr[row_begin + i] - h_ptr[row_begin], i in [0, rows]. */
 int spmm_b200_rebase_ptr(const int *h_ptr, int row_begin, int row_end, int *out_ptr);
+
+/* ---- sharded host I/O, one process per GPU (hpc_b200/csrc/replicate.cu) ------------------------------------
+ * The end-to-end call for a row partition over `world` ranks: B is replicated over NVLink instead of being uploaded
+ * whole by every rank. peers_b[r] is rank r's full copy of B (b_rows * feat_in floats, 16-byte aligned) as mapped
+ * into THIS process (symmetric / peer-mapped memory; peers_b[rank] is the local one), multicast_b the NVLS multicast
+ * address of the same buffers or NULL, peers_flags[r] rank r's 2 * world zero-initialised uint32 flag words, mapped
+ * the same way. world <= 16; world = 0 switches the mode off. Allocation and address exchange are the caller's
+ * (bench.py: torch.distributed._symmetric_memory). */
+int spmm_b200_set_replicate(spmm_b200_t h, int world, int rank, float *const *peers_b, float *multicast_b,
+                            unsigned int *const *peers_flags);
+
+/* Collective over the ranks (every rank calls it once per step, in the same order): upload this rank's slice
+ * h_vin_rows = rows [row_begin, row_begin + row_count) of B from the host, store it into every rank's copy of B
+ * (multimem.st through the multicast address, else one peer store per rank), cross-rank flag barrier, SpMM passes
+ * over the local copy, download this rank's block of C (num_v * feat_in floats) into h_vout, synchronise. The
+ * slices of all ranks must tile [0, b_rows). PCIe carries 4*row_count*feat_in bytes in and 4*num_v*feat_in out. */
+int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin_rows, int row_begin, int row_count, float *h_vout,
+                               void *stream);
+
+/* ---- multi-GPU driver, one process and N devices (hpc_b200/csrc/multi.cu) -------------------
+ * No reference counterpart (single GPU; `// extern ncclComm_t* comms;`, PA4/handout/include/util.h:30). */
+typedef struct spmm_b200_mg *spmm_b200_mg_t;
+
+/* HOST CSR arrays of the whole graph. Rows are cut into n_devices contiguous blocks balanced by nnz
+ * (spmm_b200_partition_rows), each block is uploaded to its device (devices[g], or g when devices is NULL; the same
+ * device may be listed more than once), which also gets a full-size B, its block of C and one operator handle with
+ * b_rows = num_v. n_devices <= 16. Peer access between the devices is switched on when they offer it. */
+int spmm_b200_mg_create(const int *h_ptr, const int *h_idx, const float *h_val, int num_v, int num_e, int feat_in,
+                        int n_devices, const int *devices, spmm_b200_mg_t *out);
+/* spmm_b200_set_option on every device's handle. */
+int spmm_b200_mg_set_option(spmm_b200_mg_t m, const char *name, long long value);
+/* spmm_b200_preprocess on every device. */
+int spmm_b200_mg_preprocess(spmm_b200_mg_t m);
+/* n_devices, bounds int32[n_devices + 1] (device g owns rows [bounds[g], bounds[g+1])), whether peer access is on.
+ * Any of the outputs may be NULL. */
+int spmm_b200_mg_info(spmm_b200_mg_t m, int *n_devices, int *bounds, int *peer_access);
+/* Device g's buffers: its full B (num_v * feat_in), its block of C, the full C (NULL until set_fused / allgather /
+ * swap allocated it) and its operator handle. Any of the outputs may be NULL. */
+int spmm_b200_mg_device_buffers(spmm_b200_mg_t m, int g, float **d_b, float **d_c_block, float **d_c_full, spmm_b200_t *op);
+/* Host buffers in and out: h_vin = B (num_v * feat_in), h_vout = C (num_v * feat_in), pinned for overlap. Device g
+ * uploads rows [g*num_v/N, (g+1)*num_v/N) of B and stores them into every device's copy through peer mappings
+ * (cudaMemcpyPeerAsync without peer access), every device runs its block and downloads it. Synchronises. */
+int spmm_b200_mg_run_host(spmm_b200_mg_t m, const float *h_vin, float *h_vout);
+/* Device-resident step: C block = A block x (the device's B buffer) on every device, asynchronously. */
+int spmm_b200_mg_run(spmm_b200_mg_t m);
+/* Waits for everything queued on every device. */
+int spmm_b200_mg_sync(spmm_b200_mg_t m);
+/* Stacked layers without a collective: with on != 0 every following mg_run also stores each finished C row into
+ * every device's full C (spmm_b200_set_gather over the peer mappings); after mg_sync the full C is complete
+ * everywhere. Needs peer access and feat_in % 4 == 0. */
+int spmm_b200_mg_set_fused(spmm_b200_mg_t m, int on);
+/* The baseline for the same step: all-gather-v of the C blocks into every device's full C with NCCL (one grouped
+ * ncclBroadcast per row block; libnccl.so.2 is opened on first use), asynchronously on the devices' streams. */
+int spmm_b200_mg_allgather(spmm_b200_mg_t m);
+/* Next layer: the full C becomes B and the old B becomes the full-C buffer (after mg_sync). */
+int spmm_b200_mg_swap(spmm_b200_mg_t m);
+int spmm_b200_mg_destroy(spmm_b200_mg_t m);
 
 #ifdef __cplusplus
 }

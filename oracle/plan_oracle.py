@@ -10,7 +10,7 @@ independently written restatement of the plan's published definition:
   order  = rows by (bucket descending, row ascending), or natural order when reorder = 0
   row_perm = non-heavy rows in order; heavy rows in order are cut into
   nseg = ceil(deg/seg_len) segments [begin + j*deg//nseg, begin + (j+1)*deg//nseg);
-  panel = segments' (col, val-bits) pairs back to back, each padded to an even entry count.
+  panel = segments' (col, val-bits) pairs back to back, each padded with nops to a multiple of 4 * (32 / lanes) entries.
   lpanel / ltask = the rows of row_perm as a stream of header + entries, packed into equal-sized tasks
   (pack_light); split / column blocks = rows cut at the boundaries of nb bands of B rows (split_rows),
   one plan per band.

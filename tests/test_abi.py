@@ -40,6 +40,39 @@ def test_status_codes_without_gpu():
     assert lib.spmm_b200_destroy(h) == 0
 
 
+def test_feat_zero_and_b_rows_without_gpu():
+    """feat_in = 0 is accepted by create: preprocess must build an empty plan (no division by lanes = 0, no CUDA call)
+    and run is a no-op; b_rows is part of the plan, so changing it afterwards invalidates it."""
+    from hpc_b200._lib import lib
+    h = ctypes.c_void_p()
+    dummy = (ctypes.c_int * 6)()
+    assert lib.spmm_b200_create(dummy, None, None, 5, 0, 0, ctypes.byref(h)) == 0
+    assert lib.spmm_b200_preprocess(h, None, None, None) == 0
+    assert lib.spmm_b200_run(h, None, None, None) == 0
+    assert lib.spmm_b200_refresh_values(h, None) == 0
+    assert lib.spmm_b200_set_option(h, b"b_rows", 7) == 0
+    assert lib.spmm_b200_run(h, None, None, None) == -2
+    assert lib.spmm_b200_destroy(h) == 0
+
+
+def test_host_only_graph_library_matches():
+    """libspmm_b200_graph.so (graph.cpp alone, what bench.py's CPU reference arm loads) has no CUDA dependency and
+    generates the same graph as the main library."""
+    import subprocess
+    import numpy as np
+    import hpc_b200 as H
+    path = os.path.join(ROOT, "hpc_b200", "libspmm_b200_graph.so")
+    needed = subprocess.run(["objdump", "-p", path], capture_output=True, text=True).stdout
+    assert "libcudart" not in needed and "libcuda" not in needed
+    g = ctypes.CDLL(path)
+    nv, nnz, mx, tk, zp, lp, win = H.GRAPH_SHAPES["c0"]
+    ptr, idx = np.empty(nv + 1, np.int32), np.empty(nnz, np.int32)
+    g.spmm_b200_gen_graph.argtypes = [ctypes.c_int, ctypes.c_longlong] + [ctypes.c_int] * 5 + [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+    assert g.spmm_b200_gen_graph(nv, nnz, mx, tk, zp, lp, win, 123, ptr.ctypes.data, idx.ctypes.data) == 0
+    p2, i2 = H.gen_named_graph("c0")
+    assert np.array_equal(ptr, p2) and np.array_equal(idx, i2)
+
+
 def test_product_does_not_import_oracle():
     """The product package never references oracle/ (no CPU fallback on the product path)."""
     pkg = os.path.join(ROOT, "hpc_b200")

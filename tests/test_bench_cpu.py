@@ -34,3 +34,14 @@ def test_byte_accounting():
     assert bench.bytes_min(m, nnz, k) == 4 * (m + 1) + 8 * nnz + 8 * m * k
     assert bench.bytes_gather(m, nnz, k) == 4 * (m + 1) + 8 * nnz + 4 * nnz * k + 4 * m * k
     assert bench.bytes_min(100, 10, 4, b_rows=1000) == 4 * 101 + 80 + 4 * 1000 * 4 + 4 * 100 * 4
+
+
+def test_reference_arm_loads_no_product_kernel():
+    """The CPU arm generates its graph from the host-only library: libspmm_b200.so (the product kernels) is never mapped."""
+    code = ("import bench, numpy as np; p, i = bench.host_gen_named_graph('c0', 2); "
+            "maps = open('/proc/self/maps').read(); "
+            "assert 'libspmm_b200_graph.so' in maps and 'libspmm_b200.so' not in maps and 'hpc_b200/__init__' not in str(list(__import__('sys').modules)); "
+            "c = bench.workload_config('c0_k32', p); print(sorted(c))")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "hpc_b200" not in [m for m in r.stdout.split()]

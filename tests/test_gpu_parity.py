@@ -552,6 +552,177 @@ def test_products_k256_full_size_properties():
     _full_size_properties("products", 256)
 
 
+def _abs_sum_device(g, vin, M, K, chunk=1 << 20):
+    """sum_i |B[idx_i, j] * val_i| per output element, on the device, in nnz chunks (the tolerance scale)."""
+    deg = (g.ptr[1: M + 1] - g.ptr[:M]).long()
+    rows = torch.repeat_interleave(torch.arange(M, device=DEV), deg)
+    ab = torch.zeros(M, K, device=DEV)
+    b = vin.view(-1, K)
+    for e0 in range(0, g.num_e, chunk):
+        e1 = min(g.num_e, e0 + chunk)
+        ab.index_add_(0, rows[e0:e1], (b[g.idx[e0:e1].long()] * g.val[e0:e1, None]).abs_())
+    return ab
+
+
+@pytest.mark.skipif(not refshim.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("shape", ["reddit", "products"])
+def test_full_output_against_reference_kernel_k256(shape):
+    """BASELINE configs 3-4, ALL M*K elements (the reference validates every element: test_spmm.cu:31-44): the engine
+    against the unmodified spmm_kernel_ref on identical device inputs — whole rows bit-equal, split rows within
+    1e-5 * sum|terms|, and the reference's own criterion. No sampling."""
+    K = 256
+    ptr, idx = H.gen_named_graph(shape)
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    M = g.num_v
+    op = H.SpMMB200(g, K)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    ref_out = torch.full((M * K,), float("nan"), device=DEV)
+    refshim.ref_spmm(g.ptr, g.idx, g.val, vin, ref_out, M, g.num_e, K)
+    torch.cuda.synchronize()
+    got, ref = vout[: M * K].view(M, K), ref_out.view(M, K)
+    whole = torch.ones(M, dtype=torch.bool, device=DEV)
+    heavy = sorted(op.heavy_row_set())
+    if heavy:
+        whole[torch.tensor(heavy, device=DEV)] = False
+    assert int(whole.sum()) + len(heavy) == M
+    assert torch.equal(got[whole].view(torch.int32), ref[whole].view(torch.int32)), "whole rows must be bit-exact"
+    ab = _abs_sum_device(g, vin, M, K)
+    err = (got.double() - ref.double()).abs()
+    assert bool((err <= TOL * ab.double() + 1e-30).all()), float((err / (ab.double() + 1e-30)).max())
+    assert refshim.ref_valid(vout, ref_out, M * K) < M * K // 10000 + 1
+    info = op.plan_info()
+    print(f"{shape} K={K}: {M - len(heavy)} whole rows bit-equal, {len(heavy)} split rows max rel "
+          f"{float((err / (ab.double() + 1e-30)).max()):.2e}, col_blocks={info['n_col_blocks']}")
+    op.close()
+
+
+def test_refresh_values_after_in_place_update():
+    """The plan snapshots idx/val into its panels (spmm_b200.h: SNAPSHOT); refresh_values re-stages them without a new
+    plan. The reference's SpMMOpt::run reads idx/val live (PA4/workspace/src/spmm_opt.cu:22-25)."""
+    ptr, idx = H.gen_named_graph("c0")
+    for K, opts in ((32, {"seg_len": 64}), (256, {"col_blocks": 3, "seg_len": 32}), (33, {})):
+        g, vin, vout = dev_inputs(ptr, idx, K)
+        op = H.SpMMB200(g, K, **opts)
+        op.preprocess(vin, vout)
+        op.run(vin, vout)
+        g.val.mul_(-3.0)                       # edge re-weighting in place
+        op.refresh_values()
+        op.run(vin, vout)
+        torch.cuda.synchronize()
+        got = vout[: g.num_v * K].cpu().numpy().reshape(g.num_v, K)
+        check_against_oracle(ptr, idx, K, op, g, vin, got)
+        op.close()
+
+
+def test_b_rows_change_invalidates_plan_and_bands_stay_inside_b():
+    ptr, idx = H.gen_named_graph("c0")
+    K = 32
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    op = H.SpMMB200(g, K)
+    op.preprocess(vin, vout)
+    op.set_option("b_rows", g.num_v + 8)
+    with pytest.raises(H.SpmmB200Error) as e:
+        op.run(vin, vout)
+    assert e.value.code == -2
+    op.close()
+    # 10 rows of B, 7 requested bands: ceil(10/7) = 2 rows per band -> 5 bands, none outside B
+    ptr2 = np.arange(0, 11, dtype=np.int32) * 3
+    idx2 = np.tile(np.array([0, 4, 9], np.int32), 10)
+    op, g2, vin2, vout2, got = run_engine(ptr2, idx2, 8, col_blocks=7)
+    for b in range(op.plan_info()["n_col_blocks"]):
+        info = op.plan_info(b)
+        assert 0 <= info["col_begin"] < info["col_end"] <= 10
+    assert op.plan_info()["n_col_blocks"] == 5
+    check_against_oracle(ptr2, idx2, 8, op, g2, vin2, got)
+    h_in, h_out = vin2.cpu().pin_memory(), torch.empty(80).pin_memory()
+    op.run_host(h_in, h_out)
+    assert np.array_equal(h_out.numpy().reshape(10, 8).view(np.int32), got.view(np.int32))
+    op.close()
+
+
+def test_feat_zero_is_a_no_op():
+    ptr, idx = H.gen_named_graph("c0")
+    g, vin, vout = dev_inputs(ptr, idx, 4)
+    op = H.SpMMB200(g, 0)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    op.set_feat(4)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    torch.cuda.synchronize()
+    check_against_oracle(ptr, idx, 4, op, g, vin, vout[: g.num_v * 4].cpu().numpy().reshape(-1, 4))
+    op.close()
+
+
+# ---- multi-GPU driver behind the C ABI (spmm_b200_mg_*) -----------------------------------------------------
+
+def _mg_devices():
+    n = torch.cuda.device_count()
+    cases = [[0], [0, 0, 0]]            # one box GPU listed three times exercises partition, push and gather logic
+    if n >= 2:
+        cases.append(list(range(min(n, 8))))
+    return cases
+
+
+@pytest.mark.parametrize("shape,K", [("c0", 32), ("arxiv", 256)])
+def test_mg_run_host_and_stacked_layers(shape, K):
+    ptr, idx = H.gen_named_graph(shape)
+    M, nnz = len(ptr) - 1, len(idx)
+    val = O.fill_normal(nnz, 123, 1)
+    b = O.fill_normal(M * K, 123, 2)
+    g, vin, vout = dev_inputs(ptr, idx, K, val=val, b=b)
+    op = H.SpMMB200(g, K)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    vout2 = torch.empty_like(vout)
+    op.run(vout, vout2)                                  # second stacked layer on one GPU
+    torch.cuda.synchronize()
+    want1, want2 = vout[: M * K].cpu(), vout2[: M * K].cpu()
+    op.close()
+    for devs in _mg_devices():
+        mg = H.MultiGpuSpMM(ptr, idx, val, K, devices=devs)
+        info = mg.info()
+        assert info["n_devices"] == len(devs) and info["bounds"][0] == 0 and info["bounds"][-1] == M
+        assert np.array_equal(info["bounds"], H.partition_rows(ptr, len(devs)))
+        mg.preprocess()
+        h_in = torch.from_numpy(b).pin_memory()
+        h_out = torch.full((M * K,), float("nan")).pin_memory()
+        for _ in range(2):                               # twice: the second call orders its pushes after the first's passes
+            mg.run_host(h_in, h_out)
+        assert torch.equal(h_out.view(torch.int32), want1.view(torch.int32)), devs
+        # stacked layers, device-resident: NCCL (or copy) all-gather-v vs the fused epilogue — bit-identical
+        for fused in (False, True):
+            mg.set_fused(fused)
+            mg.run_host(h_in, h_out)                     # B = input on every device again
+            mg.run()
+            if not fused:
+                mg.allgather()
+            mg.sync()
+            mg.swap()                                    # layer 1's C is layer 2's B
+            mg.run()
+            if not fused:
+                mg.allgather()
+            mg.sync()
+            for gdev in range(len(devs)):
+                bufs = mg.device_buffers(gdev)
+                full = torch.empty(M * K, device=f"cuda:{devs[gdev]}")
+                _copy_from_ptr(full, bufs["c_full"], devs[gdev])
+                assert torch.equal(full.cpu().view(torch.int32), want2.view(torch.int32)), (devs, fused, gdev)
+            mg.swap()
+        mg.close()
+
+
+def _copy_from_ptr(dst, src_ptr, device):
+    """device-to-device copy from a raw pointer (the mg driver's buffers are not torch tensors)."""
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    with torch.cuda.device(device):
+        torch.cuda.synchronize()
+        rc = rt.cudaMemcpy(C.c_void_p(dst.data_ptr()), C.c_void_p(src_ptr), C.c_size_t(dst.numel() * 4), 3)
+        assert rc == 0, rc
+
+
 # ---- the reference's test driver, restated without gtest (tests/cpp/unit_tests.cpp) ---------------------
 
 def test_cpp_harness_validation_and_timing(tmp_path):
