@@ -526,13 +526,13 @@ def run_b200(args):
         call_name = "spmm_b200_run_host (pinned B in, C out; CSR + plan resident, as in the reference harness)"
     else:
         sh.enable_sharded_host_io()
-        up0, upn = sh.up_begin, sh.up_rows
-        h_in = torch.empty(max(1, upn * k), dtype=torch.float32).pin_memory()
-        h_in[: upn * k].copy_(vin[up0 * k: (up0 + upn) * k].cpu())
-        call = lambda: sh.run_host_sharded(h_in, h_out)   # H2D(B slice) -> NVLink replicate -> kernels -> D2H(C block)
-        h2d = 4 * upn * k
-        call_name = ("spmm_b200_run_host_sharded (each rank uploads 1/N of B's rows and stores them into every rank's copy "
-                     f"over NVLink [{'multimem.st' if sh.rep_multicast else 'peer stores'}], flag barrier, passes, C block out)")
+        h_in = torch.empty(m * k, dtype=torch.float32).pin_memory()   # B on the host; this rank reads only its share of it
+        h_in.copy_(vin.cpu())
+        call = lambda: sh.run_host_sharded(h_in, h_out)   # H2D(B share) -> NVLink replicate -> kernels -> C block out
+        h2d = call()                                      # bytes this rank copies per call, counted by the library
+        call_name = ("spmm_b200_run_host_sharded (each rank uploads 1/N of every ~48 MB chunk of B and stores it into every rank's copy "
+                     f"over NVLink [{'multimem.st' if sh.rep_multicast else 'peer stores'}], per-chunk flag barrier overlapped with "
+                     "the column-block passes, final rows stored straight into the pinned C block)")
     for _ in range(2):
         call()
     ctx.barrier()

@@ -64,7 +64,8 @@ SIGNATURES = {
     "spmm_b200_partition_rows": (_I, [_P, _I, _I, _P]),
     "spmm_b200_rebase_ptr": (_I, [_P, _I, _I, _P]),
     "spmm_b200_set_replicate": (_I, [_P, _I, _I, C.POINTER(_P), _P, C.POINTER(_P)]),
-    "spmm_b200_run_host_sharded": (_I, [_P, _P, _I, _I, _P, _P]),
+    "spmm_b200_run_host_sharded": (_I, [_P, _P, _P, _P]),
+    "spmm_b200_replicate_h2d_bytes": (_LL, [_P]),
     "spmm_b200_mg_create": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, C.POINTER(_P)]),
     "spmm_b200_mg_set_option": (_I, [_P, C.c_char_p, _LL]),
     "spmm_b200_mg_preprocess": (_I, [_P]),

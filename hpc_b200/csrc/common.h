@@ -38,7 +38,8 @@ struct RunArgs {
     const int *idx;
     const float *val;
     const float *vin;
-    float *vout;
+    float *vout;     // C: partial chains between column-block passes, and final rows unless cfinal differs
+    float *cfinal;   // where FINAL rows are stored (= vout, or device-mapped pinned host memory: run_host's zero-copy output)
     int feat;        // K
     int kslice;      // feature columns per pass
     int n_slices;
@@ -107,7 +108,8 @@ struct spmm_b200_handle {
     const int *d_idx = nullptr;
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
-    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = -1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0;
+    long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = -1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0,
+              opt_zero_copy = 1;
     int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
@@ -125,9 +127,13 @@ struct spmm_b200_handle {
     float *rep_mc = nullptr;
     unsigned int *rep_flags[spmm_b200::kMaxGather] = {nullptr};
     unsigned int rep_epoch = 0;
+    long long rep_h2d_bytes = 0;   // host-to-device bytes of the last run_host_sharded call
 };
 
 namespace spmm_b200 {
+
+// capi.cu
+float *host_out_mapping(const spmm_b200_handle *h, float *h_vout);
 
 // preprocess.cu
 int build_plan(spmm_b200_handle *h, cudaStream_t stream);
@@ -137,8 +143,10 @@ int refresh_panels(spmm_b200_handle *h, cudaStream_t stream);
 // spmm_kernels.cu
 // band_ready: NULL, or one event per column block that the stream waits on before that block's pass
 // (run_host uploads B band by band on a second stream while earlier passes compute)
+// cfinal: NULL, or where the final rows go instead of vout (the last pass stores them there; earlier passes keep
+// their partial chains in vout)
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
-                int *launches, const cudaEvent_t *band_ready = nullptr);
+                int *launches, const cudaEvent_t *band_ready = nullptr, float *cfinal = nullptr);
 int resident_warps(int lanes, int vec, int tune, int block);
 int launch_check_cols(const int *d_idx, long long nnz, int b_rows, int *d_bad, cudaStream_t stream);
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,

@@ -458,9 +458,9 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         bp.col_end = nb > 1 ? (b + 1 == nb ? b_rows : (b + 1) * cols_per_block) : b_rows;
         const int *rb = nb > 1 ? split.data() + (size_t)b * M : ptr.data();
         const int *re = nb > 1 ? split.data() + (size_t)(b + 1) * M : ptr.data() + 1;
-        // passes after the first skip rows without nonzeros in their band — except the last pass in
-        // stacked-layer mode, which must touch (and forward) every row
-        const bool skip_empty = b > 0 && !(h->n_gather > 0 && b + 1 == nb);
+        // passes after the first skip rows without nonzeros in their band — except the last pass, which lists every
+        // row: it is the one that delivers final rows (to C, to the stacked-layer targets, to run_host's host buffer)
+        const bool skip_empty = b > 0 && b + 1 != nb;
         int rc = build_block(h, bp, rb, re, skip_empty, stream);
         if (rc) return rc;
     }

@@ -6,6 +6,9 @@
 // `multimem.st` per 16 bytes through the NVLS multicast address when there is one, else one `st.global` per peer —
 // and a device-side flag barrier over the same peer mappings orders the pushes against the SpMM passes. PCIe then
 // carries 4·b_rows·K/N bytes in and 4·rows_g·K bytes out per rank instead of the whole B on every rank.
+#include <algorithm>
+#include <vector>
+
 #include "common.h"
 
 namespace spmm_b200 {
@@ -116,10 +119,21 @@ int spmm_b200_set_replicate(spmm_b200_t h, int world, int rank, float *const *pe
     return 0;
 }
 
-int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin_rows, int row_begin, int row_count, float *h_vout,
-                               void *stream) {
-    if (!h || row_begin < 0 || row_count < 0 || (row_count > 0 && !h_vin_rows) || !h_vout) {
-        set_error("spmm_b200_run_host_sharded: bad arguments");
+// B is cut into n_chunks equal row chunks by a rule every rank evaluates identically (b_rows and feat_in only: about
+// 48 MB each, the column-block band size, so chunks and bands coincide whenever a rank's plan uses column blocks);
+// rank g brings in the g-th of `world` equal pieces of every chunk.
+static int replicate_chunks(long long b_rows, int feat) {
+    const long long bytes = b_rows * feat * 4ll, band = 48ll << 20;
+    long long n = (bytes + band - 1) / band;
+    if (n < 1) n = 1;
+    if (n > 16) n = 16;
+    if (n > b_rows) n = b_rows > 0 ? b_rows : 1;
+    return (int)n;
+}
+
+int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin, float *h_vout, void *stream) {
+    if (!h || !h_vin || !h_vout) {
+        set_error("spmm_b200_run_host_sharded: null argument");
         return SPMM_B200_EINVAL;
     }
     if (h->rep_world <= 0) {
@@ -130,12 +144,13 @@ int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin_rows, int row_b
         set_error("spmm_b200_run_host_sharded: preprocess has not been called");
         return SPMM_B200_ESTATE;
     }
-    const int b_rows = h->b_rows > 0 ? h->b_rows : h->num_v;
-    if ((long long)row_begin + row_count > b_rows || h->feat % 4 != 0) {
-        set_error("spmm_b200_run_host_sharded: rows [%d, %d) outside B (%d rows), or feat_in %% 4 != 0", row_begin,
-                  row_begin + row_count, b_rows);
+    if (h->feat % 4 != 0 || h->feat == 0) {
+        set_error("spmm_b200_run_host_sharded: needs feat_in %% 4 == 0");
         return SPMM_B200_EINVAL;
     }
+    const int b_rows = h->b_rows > 0 ? h->b_rows : h->num_v;
+    const int world = h->rep_world, rank = h->rep_rank;
+    const Plan &p = h->plan;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)h->num_v * h->feat;
     if (h->stage_elems < n) {
@@ -145,23 +160,62 @@ int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin_rows, int row_b
         if (n) SB_CUDA(cudaMalloc((void **)&h->d_stage_out, n * sizeof(float)));
         h->stage_elems = n;
     }
-    float *local_b = h->rep_b[h->rep_rank];
-    const long long off = (long long)row_begin * h->feat, cnt = (long long)row_count * h->feat;
-    const unsigned int epoch = ++h->rep_epoch;
+    const int n_chunks = replicate_chunks(b_rows, h->feat);
+    const int chunk_rows = (b_rows + n_chunks - 1) / n_chunks;
+    if (!h->copy_stream) {
+        int lo = 0, hi = 0;
+        SB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        // above the passes: a pending push or barrier must not queue behind the CTAs of a pass that does not need it
+        SB_CUDA(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi));
+    }
+    while ((int)h->band_events.size() < std::max(n_chunks, p.n_col_blocks) + 1) {
+        cudaEvent_t e;
+        SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->band_events.push_back(e);
+    }
+    float *local_b = h->rep_b[rank];
+    cudaStream_t c = h->copy_stream;
     int rc;
-    // my slice: only my own passes read it, and those of the previous call are behind us on this stream
-    if (cnt) SB_CUDA(cudaMemcpyAsync(local_b + off, h_vin_rows, (size_t)cnt * sizeof(float), cudaMemcpyHostToDevice, s));
-    // phase 0: every rank is done reading its copy of B (previous call) before anybody overwrites a row of it
-    if ((rc = launch_xrank_barrier(h->rep_flags, h->rep_world, h->rep_rank, 0, epoch, s))) return rc;
-    if ((rc = launch_push_rows(local_b + off, off, cnt, h->rep_world, h->rep_b, h->rep_rank, h->rep_mc, s))) return rc;
-    // phase 1: every rank's slice has landed everywhere
-    if ((rc = launch_xrank_barrier(h->rep_flags, h->rep_world, h->rep_rank, 1, epoch, s))) return rc;
+    // the copy stream starts behind whatever is queued on the caller's stream (the previous call's passes)
+    SB_CUDA(cudaEventRecord(h->band_events[n_chunks], s));
+    SB_CUDA(cudaStreamWaitEvent(c, h->band_events[n_chunks], 0));
+    // phase 0: every rank is done gathering from its copy of B (previous call) before anybody overwrites a row of it
+    const unsigned int call = ++h->rep_epoch;
+    if ((rc = launch_xrank_barrier(h->rep_flags, world, rank, 0, call, c))) return rc;
+    long long h2d = 0;
+    for (int ck = 0; ck < n_chunks; ++ck) {
+        const long long c0 = (long long)ck * chunk_rows, c1 = std::min<long long>(b_rows, c0 + chunk_rows);
+        const long long r0 = c0 + (c1 - c0) * rank / world, r1 = c0 + (c1 - c0) * (rank + 1) / world;
+        const long long off = r0 * h->feat, cnt = (r1 - r0) * h->feat;
+        if (cnt) {
+            SB_CUDA(cudaMemcpyAsync(local_b + off, h_vin + off, (size_t)cnt * sizeof(float), cudaMemcpyHostToDevice, c));
+            if ((rc = launch_push_rows(local_b + off, off, cnt, world, h->rep_b, rank, h->rep_mc, c))) return rc;
+            h2d += cnt * 4;
+        }
+        // phase 1, one epoch per chunk: every rank's piece of this chunk has landed everywhere
+        const unsigned int epoch = (call - 1) * (unsigned int)n_chunks + (unsigned int)ck + 1u;
+        if ((rc = launch_xrank_barrier(h->rep_flags, world, rank, 1, epoch, c))) return rc;
+        SB_CUDA(cudaEventRecord(h->band_events[ck], c));
+    }
+    h->rep_h2d_bytes = h2d;
     if (n) {
-        if ((rc = launch_spmm(h, local_b, h->d_stage_out, s, &h->plan.launches))) return rc;
-        SB_CUDA(cudaMemcpyAsync(h_vout, h->d_stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        // pass b gathers from B rows [col_begin, col_end): it waits for the last chunk that holds any of them
+        std::vector<cudaEvent_t> ready((size_t)p.n_col_blocks);
+        for (int b = 0; b < p.n_col_blocks; ++b) {
+            const int last_row = std::max(0, std::min(b_rows, p.blocks[b].col_end) - 1);
+            ready[b] = h->band_events[std::min(n_chunks - 1, last_row / chunk_rows)];
+        }
+        float *out_map = host_out_mapping(h, h_vout);   // pinned output: the last pass stores final rows straight into it
+        if ((rc = launch_spmm(h, local_b, h->d_stage_out, s, &h->plan.launches, ready.data(), out_map))) return rc;
+        if (!out_map) SB_CUDA(cudaMemcpyAsync(h_vout, h->d_stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+        SB_CUDA(cudaStreamWaitEvent(s, h->band_events[n_chunks - 1], 0));
     }
     SB_CUDA(cudaStreamSynchronize(s));
+    SB_CUDA(cudaStreamSynchronize(c));
     return 0;
 }
+
+long long spmm_b200_replicate_h2d_bytes(spmm_b200_t h) { return h ? h->rep_h2d_bytes : 0; }
 
 }  // extern "C"

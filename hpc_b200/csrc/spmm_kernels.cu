@@ -50,7 +50,7 @@ __device__ __forceinline__ void st_c_row(float *p, const float4 &v) {
 // A finished C row piece: to vout, and in stacked-layer mode to every rank's copy of the next layer's B —
 // one multimem.st through the NVLS multicast address when there is one, else one st.global per peer-mapped buffer.
 __device__ __forceinline__ void st_final(const RunArgs &a, int row, int col, const float4 &v) {
-    st_c_row(a.vout + (size_t)row * a.feat + col, v);
+    st_c_row(a.cfinal + (size_t)row * a.feat + col, v);
     if (a.n_gather) {
         const size_t off = (size_t)(a.gather_row0 + row) * a.feat + col;
         if (a.gather_mc) {
@@ -549,7 +549,7 @@ int slots_shape(int block, int tune) {
 }  // namespace
 
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
-                int *launches, const cudaEvent_t *band_ready) {
+                int *launches, const cudaEvent_t *band_ready, float *cfinal) {
     const Plan &p = h->plan;
     *launches = 0;
     if (h->num_v == 0 || h->feat == 0) return 0;
@@ -579,6 +579,7 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         a.heavy_seg0 = bp.d_heavy_seg0;
         a.accumulate = blk > 0;
         const bool last = blk + 1 == p.n_col_blocks;   // only the last pass produces final rows
+        a.cfinal = last && cfinal ? cfinal : vout;
         a.n_gather = last ? h->n_gather : 0;
         for (int t = 0; t < kMaxGather; ++t) a.gather[t] = h->gather[t];
         a.gather_mc = h->gather_mc;

@@ -141,7 +141,7 @@ class ShardedSpMM:
     def enable_sharded_host_io(self, use_multicast: bool = True) -> torch.Tensor:
         """Allocates this rank's full copy of B and the barrier flag words as symmetric memory (torch's
         `_symmetric_memory`: allocation + address exchange only) and hands every rank's mapping to the operator
-        (spmm_b200_set_replicate). Rank g then uploads rows [g*num_v/world, (g+1)*num_v/world) of B."""
+        (spmm_b200_set_replicate). Rank g then uploads the g-th of `world` pieces of every ~48 MB chunk of B."""
         import torch.distributed._symmetric_memory as symm_mem
         group = self.group or dist.group.WORLD
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -156,14 +156,12 @@ class ShardedSpMM:
         self._rep_handles = (hb, hf)
         self.rep_multicast = bool(mc)
         self.op.set_replicate(self.world, self.rank, hb.buffer_ptrs, mc, hf.buffer_ptrs)
-        self.up_begin = self.num_v * self.rank // self.world
-        self.up_rows = self.num_v * (self.rank + 1) // self.world - self.up_begin
         return self._rep_b
 
-    def run_host_sharded(self, h_vin_rows: torch.Tensor, h_vout_local: torch.Tensor) -> None:
-        """h_vin_rows: this rank's rows [up_begin, up_begin + up_rows) of B on the host; h_vout_local: its block of
-        C. Collective: every rank calls it once per step."""
-        self.op.run_host_sharded(h_vin_rows, self.up_begin, self.up_rows, h_vout_local)
+    def run_host_sharded(self, h_vin: torch.Tensor, h_vout_local: torch.Tensor) -> int:
+        """h_vin: the whole B on the host (this rank reads only its 1/world share of every chunk); h_vout_local: its
+        block of C. Collective: every rank calls it once per step. Returns the bytes this rank uploaded."""
+        return self.op.run_host_sharded(h_vin, h_vout_local)
 
     def close(self):
         if hasattr(self.op, "close"):

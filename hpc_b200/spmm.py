@@ -133,14 +133,15 @@ class SpMMB200(SpMM):
         pf = (C.c_void_p * max(1, world))(*[int(p) for p in peers_flags])
         check(lib.spmm_b200_set_replicate(self._h, int(world), int(rank), pb, C.c_void_p(multicast_b or 0), pf))
 
-    def run_host_sharded(self, h_vin_rows: torch.Tensor, row_begin: int, row_count: int, h_vout: torch.Tensor) -> None:
-        """Collective over the ranks: upload this rank's rows of B, replicate them over NVLink, run, download the
-        local block of C, synchronise (spmm_b200_run_host_sharded)."""
-        for name, t, n in (("h_vin_rows", h_vin_rows, row_count * self.feat_in), ("h_vout", h_vout, self.num_v * self.feat_in)):
+    def run_host_sharded(self, h_vin: torch.Tensor, h_vout: torch.Tensor) -> int:
+        """Collective over the ranks: upload this rank's share of B (h_vin is the whole B on the host), replicate it
+        over NVLink, run, deliver the local block of C into h_vout, synchronise (spmm_b200_run_host_sharded).
+        Returns the host-to-device bytes this rank copied."""
+        for name, t, n in (("h_vin", h_vin, self.b_rows * self.feat_in), ("h_vout", h_vout, self.num_v * self.feat_in)):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
                 raise ValueError(f"{name}: need a contiguous host float32 tensor of >= {n} elements")
-        check(lib.spmm_b200_run_host_sharded(self._h, C.c_void_p(h_vin_rows.data_ptr()), int(row_begin), int(row_count),
-                                             C.c_void_p(h_vout.data_ptr()), _stream()))
+        check(lib.spmm_b200_run_host_sharded(self._h, C.c_void_p(h_vin.data_ptr()), C.c_void_p(h_vout.data_ptr()), _stream()))
+        return int(lib.spmm_b200_replicate_h2d_bytes(self._h))
 
     @property
     def launches_per_run(self) -> int:

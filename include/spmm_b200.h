@@ -51,6 +51,8 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "col_blocks" passes over A, each gathering from one band of B rows that fits the L2
  *               (0 = auto: 1 unless B is larger than the L2 and rows are long); needs ascending
  *               columns inside each row, otherwise falls back to 1
+ *   "zero_copy" run_host / run_host_sharded: 1 (default) = when the output buffer is pinned host memory the last pass
+ *               stores final rows straight into it (no separate device-to-host copy), 0 = always copy
  *   "tune"      measured kernel variant, 0 (default) or 1, see hpc_b200/csrc/spmm_kernels.cu
  *   "b_rows"    rows of B when A is a row block of a larger graph (0 = num_v). Part of the plan (column bounds
  *               check, 32-bit offset guard, column-block bands, run_host's copy of B): changing it after
@@ -90,15 +92,16 @@ int spmm_b200_run_profiled(spmm_b200_t h, const float *vin, float *vout, void *s
  * layer's B, mapped through NVLink peer memory — or, when `multicast` is non-NULL, once through that NVLS multicast
  * address of the same buffers (multimem.st). The all-gather of C then needs no separate collective: after the
  * kernel and a cross-rank barrier every rank holds the full C. Targets are device pointers, 16-byte aligned, of
- * b_rows * feat_in floats; n_targets <= 16; 0 switches the mode off. Set it before preprocess when column blocks
- * are in use (changing it invalidates such a plan). */
+ * b_rows * feat_in floats; n_targets <= 16; 0 switches the mode off. */
 int spmm_b200_set_gather(spmm_b200_t h, int n_targets, float *const *targets, float *multicast, long long row_offset);
 
 /* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). */
 int spmm_b200_destroy(spmm_b200_t h);
 
 /* Host-buffer convenience for callers that hold B and C on the host: H2D(vin) → run → D2H(vout)
- * on `stream`, then synchronise. The handle keeps device staging buffers of num_v*feat_in floats.
+ * on `stream`, then synchronise. The handle keeps device staging buffers of num_v*feat_in floats. With column
+ * blocks B is uploaded band by band on a second stream while earlier passes compute; when h_vout is pinned
+ * (cudaHostAlloc / cudaHostRegister) the last pass stores the final rows straight into it over PCIe.
  * (The reference's harness keeps everything on the device; this is the end-to-end call that
  * bench.py times as `e2e`.) */
 int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *stream);
@@ -239,13 +242,18 @@ int spmm_b200_rebase_ptr(const int *h_ptr, int row_begin, int row_end, int *out_
 int spmm_b200_set_replicate(spmm_b200_t h, int world, int rank, float *const *peers_b, float *multicast_b,
                             unsigned int *const *peers_flags);
 
-/* Collective over the ranks (every rank calls it once per step, in the same order): upload this rank's slice
- * h_vin_rows = rows [row_begin, row_begin + row_count) of B from the host, store it into every rank's copy of B
- * (multimem.st through the multicast address, else one peer store per rank), cross-rank flag barrier, SpMM passes
- * over the local copy, download this rank's block of C (num_v * feat_in floats) into h_vout, synchronise. The
- * slices of all ranks must tile [0, b_rows). PCIe carries 4*row_count*feat_in bytes in and 4*num_v*feat_in out. */
-int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin_rows, int row_begin, int row_count, float *h_vout,
-                               void *stream);
+/* Collective over the ranks (every rank calls it once per step, in the same order). h_vin is the WHOLE B on the
+ * host (b_rows * feat_in floats), of which this rank reads only its share: B is cut into equal row chunks of about
+ * 48 MB by a rule all ranks evaluate identically, and rank g uploads the g-th of `world` equal pieces of every chunk,
+ * stores it into every rank's copy of B (multimem.st through the multicast address, else one peer store per rank) and
+ * joins a cross-rank flag barrier per chunk — all on a second, high-priority stream, so that the upload and
+ * replication of later chunks overlap the column-block passes over earlier ones. The rank's block of C (num_v *
+ * feat_in floats) goes to h_vout: stored straight into it by the last pass when it is pinned, else copied.
+ * Synchronises. PCIe carries about 4*b_rows*feat_in/world bytes in and 4*num_v*feat_in bytes out per rank. */
+int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin, float *h_vout, void *stream);
+
+/* Host-to-device bytes the last spmm_b200_run_host_sharded call of this handle copied (bench.py's accounting). */
+long long spmm_b200_replicate_h2d_bytes(spmm_b200_t h);
 
 /* ---- multi-GPU driver, one process and N devices (hpc_b200/csrc/multi.cu) -------------------
  * No reference counterpart (single GPU; `// extern ncclComm_t* comms;`, PA4/handout/include/util.h:30). */

@@ -400,7 +400,7 @@ def test_column_block_plan_matches_oracle(shape, K, nb, seg_len):
         inf = op.plan_info(b)
         assert (inf["col_begin"], inf["col_end"]) == (b * cpb, min(M, (b + 1) * cpb))
         assert np.array_equal(got["split"], split)
-        want = P.plan(ptr, idx, val, inf["seg_len"], True, rb=split[b], re=split[b + 1], skip_empty=b > 0, k4=K // 4,
+        want = P.plan(ptr, idx, val, inf["seg_len"], True, rb=split[b], re=split[b + 1], skip_empty=0 < b < nb - 1, k4=K // 4,
                       pad=4 * (32 // inf["lanes"]))
         want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"], k4=K // 4))
         for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
