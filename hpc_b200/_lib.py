@@ -24,6 +24,7 @@ class PlanInfo(C.Structure):
         ("panel_len", C.c_longlong), ("lanes", C.c_int), ("vec", C.c_int),
         ("n_ltask", C.c_int), ("n_utask", C.c_int), ("lpanel_len", C.c_longlong), ("light_steps", C.c_int), ("reorder", C.c_int), ("resident_warps", C.c_int),
         ("n_col_blocks", C.c_int), ("col_begin", C.c_int), ("col_end", C.c_int),
+        ("persistent", C.c_int), ("n_row_groups", C.c_int), ("n_tickets", C.c_int),
     ]
 
     def as_dict(self):

@@ -33,37 +33,61 @@ struct SegDesc {
     int nnz_begin;
 };
 
-// Everything a run needs, passed to the kernel by value.
-struct RunArgs {
-    const int *idx;
+constexpr int kMaxBands = 16;    // column blocks one persistent launch can carry
+constexpr int kMaxRowGroups = 64;
+
+// What every pass of a run shares.
+struct CommonArgs {
+    const int *idx;           // scalar fallback kernel only (the vectorised kernels read the staged panels)
     const float *val;
     const float *vin;
-    float *vout;     // C: partial chains between column-block passes, and final rows unless cfinal differs
-    float *cfinal;   // where FINAL rows are stored (= vout, or device-mapped pinned host memory: run_host's zero-copy output)
-    int feat;        // K
-    int kslice;      // feature columns per pass
+    float *vout;              // C: partial chains between column-block passes, and final rows unless cfinal differs
+    float *cfinal;            // where FINAL rows are stored (= vout, or device-mapped pinned host memory: run_host's zero-copy output)
+    int feat;                 // K
+    int kslice;               // feature columns per slice
     int n_slices;
-    // light rows
-    const int4 *light_desc;   // {row, begin, deg, dst} in processing order (dst: its header's slot in lpanel)
+    // stacked-layer epilogue: final rows also go to every rank's copy of the next layer's B
+    int n_gather;             // 0 = off
+    float *gather[kMaxGather];   // peer-mapped (or local) buffers of b_rows x K floats
+    float *gather_mc;         // NVLS multicast address of the same buffers, or NULL
+    long long gather_row0;    // this handle's first row inside those buffers
+};
+
+// One column block (band of B rows) of the plan.
+struct BandArgs {
+    const int4 *light_desc;   // {row, begin, deg, dst} in processing order (scalar kernel; dst: header slot in lpanel)
     int n_light;
     const int2 *utask;        // warp tasks of one slice in scheduling order: {lpanel offset, steps per lane group}
                               // for a light-stream task, {-1 - segment, 0} for a heavy segment
     int n_utask;
     const int2 *lpanel;       // light rows as a stream: header {0x80000000|row, 0}, then {col, val}..., nop = {-1, -1}
-    // heavy rows
     const SegDesc *seg_desc;
-    const int *seg_hrow;       // segment -> index of its row in heavy_rows
-    const int *heavy_seg0;     // heavy row -> first segment (prefix, n_heavy + 1)
-    int *seg_count;            // [n_heavy][n_slices] finished-segment counters, zero between runs
+    const int *seg_hrow;      // segment -> index of its row in heavy_rows
+    const int *heavy_seg0;    // heavy row -> first segment (prefix, n_heavy + 1)
+    int *seg_count;           // [n_heavy][n_slices] finished-segment counters, zero between runs
     const int2 *panel;
-    float *part;               // [n_seg][K] partial sums
-    int n_seg;
-    int accumulate;            // 1: continue the chains from vout (column blocks after the first)
-    // stacked-layer epilogue: finished rows also go to every rank's copy of the next layer's B
-    int n_gather;              // 0 = off
-    float *gather[kMaxGather]; // peer-mapped (or local) buffers of b_rows x K floats
-    float *gather_mc;          // NVLS multicast address of the same buffers, or NULL
-    long long gather_row0;     // this handle's first row inside those buffers
+    float *part;              // [n_seg][K] partial sums
+    int accumulate;           // 1: continue the chains from vout (column blocks after the first)
+    int final;                // 1: this pass delivers final rows (cfinal, stacked-layer targets)
+};
+
+// One launch per column block.
+struct RunArgs {
+    CommonArgs c;
+    BandArgs b;
+};
+
+// One persistent launch for all column blocks: warps draw tickets; ticket order is band-major. `all` addresses the
+// bands' arrays as ONE set (each array is a single allocation, band after band), and the ticket list carries absolute
+// positions, so nothing in the task bodies is indexed by band.
+struct PersistArgs {
+    CommonArgs c;
+    BandArgs all;             // lpanel / panel / seg_desc / seg_hrow / heavy_seg0 / seg_count / part over all bands
+    const int4 *ptask;        // per ticket: {lpanel offset, or -1 - segment; steps; row group | accumulate << 16 | final << 17;
+                              //              completed tasks of that row group the task waits for}
+    int total;                // tickets
+    unsigned int *ctr;        // [0] ticket, [1] exited warps, [2 + g] completed tasks of row group g; zero between runs
+    int n_groups;
 };
 
 // The plan of one column block (the whole matrix when there is a single block).
@@ -88,6 +112,7 @@ struct BlockPlan {
     int *d_seg_count = nullptr;
     int2 *d_panel = nullptr;
     float *d_part = nullptr;
+    std::vector<int> task_group;   // host: row group of every utask entry (persistent launch)
 };
 
 struct Plan {
@@ -99,6 +124,21 @@ struct Plan {
     int *d_split = nullptr;   // [(n_col_blocks+1)][num_v] start of each column block inside each row
     std::vector<BlockPlan> blocks;
     int launches = 0;
+    // persistent single launch (all column blocks in one kernel)
+    bool persistent = false;
+    int n_groups = 1;               // row groups: band b+1's tasks of a group wait for band b's tasks of the same group
+    std::vector<int> group_row;     // [n_groups + 1] first row of each group
+    unsigned int *d_ctr = nullptr;  // [2 + n_groups] ticket, exited warps, per-group completion counters
+    int persist_grid = 0;           // CTAs of the persistent launch (all co-resident)
+    int n_ptask = 0;
+    int4 *d_ptask = nullptr;        // the ticket list
+    SegDesc *d_pseg_desc = nullptr; // segments of all bands with absolute panel offsets
+    int *d_pseg_hrow = nullptr;     // segment -> absolute heavy-row index
+    int *d_pheavy_seg0 = nullptr;   // absolute heavy row -> absolute first segment (n_heavy + 1 entries per band)
+    // arenas: one allocation per array kind, band after band (the per-band pointers above point into them)
+    int2 *d_lpanel_all = nullptr, *d_panel_all = nullptr;
+    float *d_part_all = nullptr;
+    int *d_seg_count_all = nullptr;
 };
 
 }  // namespace spmm_b200
@@ -109,7 +149,7 @@ struct spmm_b200_handle {
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
     long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = -1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0,
-              opt_zero_copy = 1;
+              opt_zero_copy = 1, opt_persistent = -1, opt_row_groups = 0;
     int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
@@ -148,6 +188,7 @@ int refresh_panels(spmm_b200_handle *h, cudaStream_t stream);
 int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
                 int *launches, const cudaEvent_t *band_ready = nullptr, float *cfinal = nullptr);
 int resident_warps(int lanes, int vec, int tune, int block);
+int persistent_grid(int lanes, int vec, int tune, int block);   // CTAs that are co-resident for the persistent kernel
 int launch_check_cols(const int *d_idx, long long nnz, int b_rows, int *d_bad, cudaStream_t stream);
 int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
                       int *d_split, int *d_unsorted, cudaStream_t stream);
@@ -171,7 +212,9 @@ int launch_xrank_barrier(unsigned int *const *flags, int world, int rank, int ph
 
 // Packs light rows (costs = deg + 1 entries each, in plan order) into stream tasks of `groups` interleaved lane-group
 // lanes with about `steps` entries each; dst[i] = lpanel slot of row i's header. Returns the lpanel length.
-long long pack_light_host(const int *cost, int n, int groups, int steps, int *dst, std::vector<int2> &tasks);
+// cut[0..n_cut): ascending row positions before which the open task is closed (row-group boundaries), or NULL.
+long long pack_light_host(const int *cost, int n, int groups, int steps, int *dst, std::vector<int2> &tasks,
+                          const int *cut = nullptr, int n_cut = 0);
 
 // lanes/vec choice for a slice width (shared by plan + launch)
 inline void shape_for_kslice(int kslice, int *lanes, int *vec) {

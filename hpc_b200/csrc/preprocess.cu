@@ -48,15 +48,21 @@ void free_plan(Plan &p) {
         cudaFree(b.d_light_desc);
         cudaFree(b.d_ltask);
         cudaFree(b.d_utask);
-        cudaFree(b.d_lpanel);
         cudaFree(b.d_heavy_rows);
         cudaFree(b.d_heavy_seg0);
         cudaFree(b.d_seg_desc);
         cudaFree(b.d_seg_hrow);
-        cudaFree(b.d_seg_count);
-        cudaFree(b.d_panel);
-        cudaFree(b.d_part);
+        // d_lpanel, d_panel, d_part, d_seg_count point into the arenas below
     }
+    cudaFree(p.d_lpanel_all);
+    cudaFree(p.d_panel_all);
+    cudaFree(p.d_part_all);
+    cudaFree(p.d_seg_count_all);
+    cudaFree(p.d_ptask);
+    cudaFree(p.d_pseg_desc);
+    cudaFree(p.d_pseg_hrow);
+    cudaFree(p.d_pheavy_seg0);
+    cudaFree(p.d_ctr);
     cudaFree(p.d_split);
     p = Plan();
 }
@@ -177,7 +183,8 @@ int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder
 // `steps` entries, the task is closed and the row opens the next one. A task's lanes are interleaved in the
 // panel — entry j of lane g sits at off + j*groups + g — and padded with nops to the longest lane rounded up to a
 // multiple of 4 steps (whole gather batches; it also keeps every task on a 16-byte boundary).
-long long pack_light_host(const int *cost, int n, int groups, int steps, int *dst, std::vector<int2> &tasks) {
+long long pack_light_host(const int *cost, int n, int groups, int steps, int *dst, std::vector<int2> &tasks, const int *cut,
+                          int n_cut) {
     tasks.clear();
     std::vector<int> fill((size_t)groups, 0);
     long long off = 0;
@@ -189,7 +196,19 @@ long long pack_light_host(const int *cost, int n, int groups, int steps, int *ds
         off += (long long)mx * groups;
         std::fill(fill.begin(), fill.end(), 0);
     };
+    int ci = 0;
     for (int i = 0; i < n; ++i) {
+        // a row-group boundary: no task spans it (the persistent launch orders column-block passes per row group)
+        bool boundary = false;
+        while (ci < n_cut && cut[ci] <= i) {
+            boundary |= cut[ci] == i;
+            ++ci;
+        }
+        if (boundary) {
+            bool any = false;
+            for (int x : fill) any |= x > 0;
+            if (any) close_task();
+        }
         int g = 0;
         for (int q = 1; q < groups; ++q)
             if (fill[q] < fill[g]) g = q;
@@ -228,127 +247,119 @@ int auto_light_steps(int groups, long long total_cost, long long slots, long lon
     return (int)(st < dflt ? st : dflt);
 }
 
-static int build_block(spmm_b200_handle *h, BlockPlan &bp, const int *rb, const int *re, int skip_empty,
-                       cudaStream_t stream) {
-    Plan &p = h->plan;
-    const int M = h->num_v, K = h->feat;
-    PrepTrace tr;
-    std::vector<int> row_perm, heavy_rows, heavy_seg0;
+// Everything the host works out for one column block before anything is allocated on the device.
+struct HostBlock {
+    std::vector<int> row_perm, heavy_rows, heavy_seg0, seg_hrow, task_group;
     std::vector<SegDesc> segs;
-    long long panel_len = 0;
-    // Row order. Degree buckets (longest first) shorten the tail and keep the lanes of a task balanced; natural
-    // order keeps neighbouring rows together, which lets a graph's locality hit in L2. Auto (-1): natural order
-    // when a full warp serves each row (no lanes to balance) and the block is at least 8 waves of tasks long (no
-    // tail to speak of) — measured 12.2 -> 11.3 ms on the products shape, neutral on reddit, and the opposite
-    // (0.14 -> 0.19 ms) on the one-wave arxiv shape, which therefore keeps the buckets (profiles/r01_sweep.md).
-    int reorder = (int)h->opt_reorder;
-    if (reorder < 0) {
-        long long total = 0;
-        for (int r = 0; r < M; ++r) total += re[r] - rb[r] + 1;
-        reorder = (p.lanes == 32 && p.slots > 0 && total >= 8ll * p.slots * 64) ? 0 : 1;
-    }
-    bp.reorder = reorder;
-    const int pad = p.scalar ? 2 : 4 * (32 / p.lanes);
-    int rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, pad, row_perm, heavy_rows, heavy_seg0,
-                            segs, &panel_len);
-    if (rc) return rc;
-    tr.lap("block: plan_rows_host");
-    bp.n_light = (int)row_perm.size();
-    bp.n_heavy = (int)heavy_rows.size();
-    bp.n_seg = (int)segs.size();
-    bp.panel_len = panel_len;
+    std::vector<int4> light;
+    std::vector<int2> ltasks, utask;
+    long long panel_len = 0, lpanel_len = 0;
+    int reorder = 1, light_steps = 0;
+    int rc = 0;
+    char err[256] = "";
+};
 
-    auto upload = [&](void **dst, const void *src, size_t bytes) -> int {
-        if (bytes == 0) return 0;
-        SB_CUDA(cudaMalloc(dst, bytes));
-        SB_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, stream));
-        return 0;
-    };
-    std::vector<int4> light((size_t)bp.n_light);
-    std::vector<int> cost((size_t)bp.n_light), dst((size_t)bp.n_light);
-    std::vector<int2> ltasks;
+// Row order of a block. Degree buckets (longest first) shorten the tail and keep the lanes of a task balanced; natural
+// order keeps neighbouring rows together, which lets a graph's locality hit in L2. Auto (-1): natural order
+// when a full warp serves each row (no lanes to balance) and the block is at least 8 waves of tasks long (no
+// tail to speak of) — measured 12.2 -> 11.3 ms on the products shape, neutral on reddit, and the opposite
+// (0.14 -> 0.19 ms) on the one-wave arxiv shape, which therefore keeps the buckets (profiles/r01_sweep.md).
+static int block_reorder(const spmm_b200_handle *h, const int *rb, const int *re) {
+    const Plan &p = h->plan;
+    if (h->opt_reorder >= 0) return (int)h->opt_reorder;
+    long long total = 0;
+    for (int r = 0; r < h->num_v; ++r) total += re[r] - rb[r] + 1;
+    return (p.lanes == 32 && p.slots > 0 && total >= 8ll * p.slots * 64) ? 0 : 1;
+}
+
+// Host part of one block: row order, segments, light-stream packing, task order, row group of every task.
+// group_row: NULL, or the n_groups + 1 row-group boundaries (natural order only).
+static void plan_block_host(const spmm_b200_handle *h, const int *rb, const int *re, int skip_empty, int reorder,
+                            const int *group_row, int n_groups, HostBlock &hb) {
+    const Plan &p = h->plan;
+    const int M = h->num_v;
+    hb.reorder = reorder;
+    const int pad = p.scalar ? 2 : 4 * (32 / p.lanes);
+    hb.rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, pad, hb.row_perm, hb.heavy_rows, hb.heavy_seg0, hb.segs,
+                           &hb.panel_len);
+    if (hb.rc) {
+        snprintf(hb.err, sizeof(hb.err), "%s", spmm_b200_last_error());
+        return;
+    }
+    const int n_light = (int)hb.row_perm.size();
+    std::vector<int> cost((size_t)n_light), dst((size_t)n_light);
     const int groups = p.scalar ? 1 : 32 / p.lanes;
-    for (int i = 0; i < bp.n_light; ++i) cost[i] = re[row_perm[i]] - rb[row_perm[i]] + 1;
-    long long lpanel_len = 0;
+    for (int i = 0; i < n_light; ++i) cost[i] = re[hb.row_perm[i]] - rb[hb.row_perm[i]] + 1;
+    // positions in row_perm where a new row group starts (row_perm ascends in natural order)
+    std::vector<int> cut;
+    if (group_row && n_groups > 1)
+        for (int g = 1; g < n_groups; ++g)
+            cut.push_back((int)(std::lower_bound(hb.row_perm.begin(), hb.row_perm.end(), group_row[g]) - hb.row_perm.begin()));
     if (!p.scalar) {
         int steps = p.light_steps;
         if (h->opt_light_steps <= 0) {
             long long total = 0;
             for (int c : cost) total += c;
-            steps = auto_light_steps(groups, total, p.slots, (long long)segs.size() * p.n_slices);
-            if (&bp == &p.blocks[0]) p.light_steps = steps;   // reported by plan_info (block 0)
+            steps = auto_light_steps(groups, total, p.slots, (long long)hb.segs.size() * p.n_slices);
         }
-        bp.light_steps = steps;
-        lpanel_len = pack_light_host(cost.data(), bp.n_light, groups, steps, dst.data(), ltasks);
-        if (lpanel_len > 0x7fffffffll) {
-            set_error("light panel too large");
-            return SPMM_B200_EINVAL;
+        hb.light_steps = steps;
+        hb.lpanel_len = pack_light_host(cost.data(), n_light, groups, steps, dst.data(), hb.ltasks, cut.data(), (int)cut.size());
+        if (hb.lpanel_len > 0x7fffffffll) {
+            hb.rc = SPMM_B200_EINVAL;
+            snprintf(hb.err, sizeof(hb.err), "light panel too large");
+            return;
         }
     }
-    tr.lap("block: pack_light_host");
-    for (int i = 0; i < bp.n_light; ++i) {
-        const int r = row_perm[i];
-        light[i] = make_int4(r, rb[r], re[r] - rb[r], p.scalar ? 0 : dst[i]);
+    hb.light.resize((size_t)n_light);
+    for (int i = 0; i < n_light; ++i) {
+        const int r = hb.row_perm[i];
+        hb.light[i] = make_int4(r, rb[r], re[r] - rb[r], p.scalar ? 0 : dst[i]);
     }
-    bp.n_ltask = (int)ltasks.size();
-    bp.lpanel_len = lpanel_len;
 
     // Scheduling order of the warp tasks. Bucketed rows: heavy segments (the longest rows) first, then the light
     // tasks. Natural order: light tasks and heavy segments merged by the row they start with, so that a heavy row
     // runs next to its neighbours (whose B rows it shares in L2) instead of ahead of everything.
-    std::vector<int2> utask;
-    utask.reserve(ltasks.size() + segs.size());
+    auto group_of = [&](int row) {
+        if (!group_row || n_groups <= 1) return 0;
+        return (int)(std::upper_bound(group_row, group_row + n_groups + 1, row) - group_row) - 1;
+    };
+    hb.utask.reserve(hb.ltasks.size() + hb.segs.size());
+    hb.task_group.reserve(hb.ltasks.size() + hb.segs.size());
     if (reorder == 0 && !p.scalar) {
         size_t li = 0, first_i = 0;   // first_i: index in row_perm of the first row of light task li
         size_t si = 0;
         auto light_first_row = [&](size_t t) {
-            while (first_i < (size_t)bp.n_light && dst[first_i] < ltasks[t].x) ++first_i;
-            return first_i < (size_t)bp.n_light ? row_perm[first_i] : 0x7fffffff;
+            while (first_i < (size_t)n_light && dst[first_i] < hb.ltasks[t].x) ++first_i;
+            return first_i < (size_t)n_light ? hb.row_perm[first_i] : 0x7fffffff;
         };
-        while (li < ltasks.size() || si < segs.size()) {
-            const int lrow = li < ltasks.size() ? light_first_row(li) : 0x7fffffff;
-            const int hrow = si < segs.size() ? segs[si].row : 0x7fffffff;
-            if (si < segs.size() && hrow < lrow) {
-                utask.push_back(make_int2(-1 - (int)si, 0));
+        while (li < hb.ltasks.size() || si < hb.segs.size()) {
+            const int lrow = li < hb.ltasks.size() ? light_first_row(li) : 0x7fffffff;
+            const int hrow = si < hb.segs.size() ? hb.segs[si].row : 0x7fffffff;
+            if (si < hb.segs.size() && hrow < lrow) {
+                hb.utask.push_back(make_int2(-1 - (int)si, 0));
+                hb.task_group.push_back(group_of(hrow));
                 ++si;
             } else {
-                utask.push_back(ltasks[li]);
+                hb.utask.push_back(hb.ltasks[li]);
+                hb.task_group.push_back(group_of(lrow));
                 ++li;
             }
         }
     } else {
-        for (size_t si = 0; si < segs.size(); ++si) utask.push_back(make_int2(-1 - (int)si, 0));
-        for (const int2 &t : ltasks) utask.push_back(t);
+        for (size_t si = 0; si < hb.segs.size(); ++si) hb.utask.push_back(make_int2(-1 - (int)si, 0));
+        for (const int2 &t : hb.ltasks) hb.utask.push_back(t);
+        hb.task_group.assign(hb.utask.size(), 0);
     }
-    bp.n_utask = (int)utask.size();
-    tr.lap("block: light_desc + utask");
-    std::vector<int> seg_hrow((size_t)bp.n_seg);
-    for (int hr = 0; hr < bp.n_heavy; ++hr)
-        for (int sgm = heavy_seg0[hr]; sgm < heavy_seg0[hr + 1]; ++sgm) seg_hrow[sgm] = hr;
-    if ((rc = upload((void **)&bp.d_row_perm, row_perm.data(), sizeof(int) * row_perm.size()))) return rc;
-    if ((rc = upload((void **)&bp.d_light_desc, light.data(), sizeof(int4) * light.size()))) return rc;
-    if ((rc = upload((void **)&bp.d_utask, utask.data(), sizeof(int2) * utask.size()))) return rc;
-    if (bp.n_ltask > 0) {
-        if ((rc = upload((void **)&bp.d_ltask, ltasks.data(), sizeof(int2) * ltasks.size()))) return rc;
-        SB_CUDA(cudaMalloc((void **)&bp.d_lpanel, sizeof(int2) * (size_t)lpanel_len));
-        SB_CUDA(cudaMemsetAsync(bp.d_lpanel, 0xFF, sizeof(int2) * (size_t)lpanel_len, stream));   // nop entries
-        if ((rc = launch_build_lpanel(bp.d_light_desc, bp.n_light, groups, K / 4, h->d_idx, h->d_val, bp.d_lpanel, stream)))
-            return rc;
-    }
-    if (bp.n_heavy > 0) {
-        if ((rc = upload((void **)&bp.d_seg_hrow, seg_hrow.data(), sizeof(int) * seg_hrow.size()))) return rc;
-        const size_t ncnt = (size_t)bp.n_heavy * p.n_slices;
-        SB_CUDA(cudaMalloc((void **)&bp.d_seg_count, sizeof(int) * ncnt));
-        SB_CUDA(cudaMemsetAsync(bp.d_seg_count, 0, sizeof(int) * ncnt, stream));
-        if ((rc = upload((void **)&bp.d_heavy_rows, heavy_rows.data(), sizeof(int) * heavy_rows.size()))) return rc;
-        if ((rc = upload((void **)&bp.d_heavy_seg0, heavy_seg0.data(), sizeof(int) * heavy_seg0.size()))) return rc;
-        if ((rc = upload((void **)&bp.d_seg_desc, segs.data(), sizeof(SegDesc) * segs.size()))) return rc;
-        SB_CUDA(cudaMalloc((void **)&bp.d_panel, sizeof(int2) * (size_t)panel_len));
-        SB_CUDA(cudaMalloc((void **)&bp.d_part, sizeof(float) * (size_t)bp.n_seg * K));
-        if ((rc = launch_build_panel(bp.d_seg_desc, bp.n_seg, K / 4, pad, h->d_idx, h->d_val, bp.d_panel, stream))) return rc;
-    }
-    SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
-    tr.lap("block: upload + panels");
+    hb.seg_hrow.resize(hb.segs.size());
+    for (int hr = 0; hr < (int)hb.heavy_rows.size(); ++hr)
+        for (int sgm = hb.heavy_seg0[hr]; sgm < hb.heavy_seg0[hr + 1]; ++sgm) hb.seg_hrow[sgm] = hr;
+}
+
+template <class T>
+static int upload_vec(T **dst, const std::vector<T> &v, cudaStream_t stream) {
+    if (v.empty()) return 0;
+    SB_CUDA(cudaMalloc((void **)dst, sizeof(T) * v.size()));
+    SB_CUDA(cudaMemcpyAsync(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, stream));
     return 0;
 }
 
@@ -371,9 +382,9 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     p.kslice = h->opt_kslice > 0 ? (int)h->opt_kslice : auto_kslice(M, K);
     if (p.scalar) p.kslice = K;
     if (p.kslice > 256) p.kslice = 256;
-    if (K > 0 && p.kslice > ((K + 3) & ~3)) p.kslice = (K + 3) & ~3;
-    p.n_slices = (K > 0) ? (K + p.kslice - 1) / p.kslice : 0;
-    if (!p.scalar && K > 0) shape_for_kslice(p.kslice, &p.lanes, &p.vec);
+    if (p.kslice > ((K + 3) & ~3)) p.kslice = (K + 3) & ~3;
+    p.n_slices = (K + p.kslice - 1) / p.kslice;
+    if (!p.scalar) shape_for_kslice(p.kslice, &p.lanes, &p.vec);
     p.seg_len = h->opt_seg_len > 0 ? (int)h->opt_seg_len : auto_seg_len(h->num_e, p.lanes);
     p.tune = (int)h->opt_tune;
     p.light_steps = h->opt_light_steps > 0 ? (int)h->opt_light_steps : 0;
@@ -384,86 +395,236 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         return SPMM_B200_EINVAL;
     }
     int nb = h->opt_col_blocks > 0 ? (int)h->opt_col_blocks : auto_col_blocks(b_rows, K, h->num_e, M);
-    if (p.scalar || M == 0 || nb < 1) nb = 1;
+    if (p.scalar || nb < 1) nb = 1;
+    if (nb > kMaxBands && h->opt_col_blocks <= 0) nb = kMaxBands;
     if (nb > b_rows) nb = b_rows > 0 ? b_rows : 1;
 
     PrepTrace tr;
     std::vector<int> ptr((size_t)M + 1, 0);
-    if (M > 0) {
-        SB_CUDA(cudaMemcpyAsync(ptr.data(), h->d_ptr, sizeof(int) * ((size_t)M + 1), cudaMemcpyDeviceToHost,
-                                stream));
-        SB_CUDA(cudaStreamSynchronize(stream));
-    }
-    if (M > 0 && (ptr[0] != 0 || ptr[M] != h->num_e)) {
+    SB_CUDA(cudaMemcpyAsync(ptr.data(), h->d_ptr, sizeof(int) * ((size_t)M + 1), cudaMemcpyDeviceToHost, stream));
+    // columns must address rows of B: one pass over idx, queued behind the copy of ptr
+    int *d_flags = nullptr, flags[2] = {0, 0};   // [0] bad column, [1] unsorted row
+    SB_CUDA(cudaMalloc((void **)&d_flags, sizeof(flags)));
+    auto with_flags = [&](int rc) {
+        cudaFree(d_flags);
+        return rc;
+    };
+    if (cudaMemsetAsync(d_flags, 0, sizeof(flags), stream) != cudaSuccess) return with_flags(cuda_fail(cudaGetLastError(), "cudaMemsetAsync", __FILE__, __LINE__));
+    int rc = launch_check_cols(h->d_idx, h->num_e, b_rows, d_flags, stream);
+    if (rc) return with_flags(rc);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return with_flags(cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__));
+    if (ptr[0] != 0 || ptr[M] != h->num_e) {
         set_error("CSR ptr is inconsistent: ptr[0]=%d ptr[num_v]=%d num_e=%d", ptr[0], ptr[M], h->num_e);
-        return SPMM_B200_EINVAL;
+        return with_flags(SPMM_B200_EINVAL);
     }
     for (int r = 0; r < M; ++r)   // whatever the row order: a negative degree would turn into out-of-bounds panel slots
         if (ptr[r + 1] < ptr[r]) {
             set_error("CSR ptr decreases at row %d", r);
-            return SPMM_B200_EINVAL;
+            return with_flags(SPMM_B200_EINVAL);
         }
+    tr.lap("ptr D2H + check_cols");
 
-    tr.lap("ptr D2H + checks");
-    {   // columns must address rows of B
-        int *d_bad = nullptr, bad = 0;
-        SB_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
-        cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), stream);
-        int rc = e == cudaSuccess ? launch_check_cols(h->d_idx, h->num_e, b_rows, d_bad, stream) : 0;
-        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(stream);
-        cudaFree(d_bad);
-        if (rc) return rc;
-        SB_CUDA(e);
-        if (bad) {
-            set_error("CSR idx holds a column outside [0, %d)", b_rows);
-            return SPMM_B200_EINVAL;
-        }
-    }
-
-    tr.lap("check_cols");
     // split every row at the column-block boundaries (needs ascending columns inside a row; a graph
     // that is not sorted falls back to a single block)
     std::vector<int> split;
     int cols_per_block = nb > 1 ? (b_rows + nb - 1) / nb : b_rows;
     if (nb > 1) nb = (b_rows + cols_per_block - 1) / cols_per_block;   // every band starts inside B (b_rows = 10, 7 bands -> 5 of 2 rows)
     if (nb > 1) {
-        int *d_unsorted = nullptr;
-        SB_CUDA(cudaMalloc((void **)&p.d_split, sizeof(int) * (size_t)(nb + 1) * M));
-        SB_CUDA(cudaMalloc((void **)&d_unsorted, sizeof(int)));
-        SB_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(int), stream));
-        int rc = launch_split_rows(h->d_ptr, h->d_idx, M, nb, cols_per_block, p.d_split, d_unsorted, stream);
-        int unsorted = 0;
-        cudaError_t e = cudaSuccess;
-        if (rc == 0) e = cudaMemcpyAsync(&unsorted, d_unsorted, sizeof(int), cudaMemcpyDeviceToHost, stream);
-        if (rc == 0 && e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        cudaFree(d_unsorted);
-        if (rc) return rc;
+        if (cudaMalloc((void **)&p.d_split, sizeof(int) * (size_t)(nb + 1) * M) != cudaSuccess)
+            return with_flags(cuda_fail(cudaGetLastError(), "cudaMalloc(split)", __FILE__, __LINE__));
+        rc = launch_split_rows(h->d_ptr, h->d_idx, M, nb, cols_per_block, p.d_split, d_flags + 1, stream);
+        if (rc) return with_flags(rc);
+        split.resize((size_t)(nb + 1) * M);
+        cudaError_t e = cudaMemcpyAsync(split.data(), p.d_split, sizeof(int) * split.size(), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return with_flags(cuda_fail(e, "cudaMemcpyAsync(split)", __FILE__, __LINE__));
+    }
+    {
+        cudaError_t e = cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(d_flags);
         SB_CUDA(e);
-        if (unsorted) {
-            cudaFree(p.d_split);
-            p.d_split = nullptr;
-            nb = 1;
-        } else {
-            split.resize((size_t)(nb + 1) * M);
-            SB_CUDA(cudaMemcpy(split.data(), p.d_split, sizeof(int) * split.size(), cudaMemcpyDeviceToHost));
-        }
+    }
+    if (flags[0]) {
+        set_error("CSR idx holds a column outside [0, %d)", b_rows);
+        return SPMM_B200_EINVAL;
+    }
+    if (nb > 1 && flags[1]) {
+        cudaFree(p.d_split);
+        p.d_split = nullptr;
+        split.clear();
+        nb = 1;
     }
     tr.lap("split_rows + D2H");
     p.n_col_blocks = nb;
     p.blocks.resize(nb);
+    auto row_begin = [&](int b) { return nb > 1 ? split.data() + (size_t)b * M : ptr.data(); };
+    auto row_end = [&](int b) { return nb > 1 ? split.data() + (size_t)(b + 1) * M : ptr.data() + 1; };
+
+    // One persistent launch for all column blocks (option "persistent": -1 auto = whenever there are several, 1 = also
+    // for a single block, 0 = one launch per block). Needs a single feature slice (K <= 256).
+    p.persistent = !p.scalar && p.n_slices == 1 && nb <= kMaxBands &&
+                   (h->opt_persistent == 1 || (h->opt_persistent < 0 && nb > 1));
+    // Row order per block, then row groups: in natural order the rows are cut into n_groups contiguous groups balanced by
+    // nonzeros; a task never spans a group, and a task of band b+1 waits for the tasks of band b that own its group.
+    // Bucketed order has no contiguous groups: one group (a band then waits for the whole band before it).
+    std::vector<int> reorder(nb);
+    bool all_natural = true;
     for (int b = 0; b < nb; ++b) {
-        BlockPlan &bp = p.blocks[b];
-        bp.col_begin = nb > 1 ? b * cols_per_block : 0;
-        bp.col_end = nb > 1 ? (b + 1 == nb ? b_rows : (b + 1) * cols_per_block) : b_rows;
-        const int *rb = nb > 1 ? split.data() + (size_t)b * M : ptr.data();
-        const int *re = nb > 1 ? split.data() + (size_t)(b + 1) * M : ptr.data() + 1;
+        reorder[b] = block_reorder(h, row_begin(b), row_end(b));
+        all_natural &= reorder[b] == 0;
+    }
+    p.n_groups = 1;
+    if (p.persistent && nb > 1 && all_natural) {
+        long long g = h->opt_row_groups > 0 ? h->opt_row_groups : 16;
+        if (g > kMaxRowGroups) g = kMaxRowGroups;
+        if (g > M) g = M;
+        p.n_groups = (int)g;
+    }
+    p.group_row.assign((size_t)p.n_groups + 1, M);
+    p.group_row[0] = 0;
+    for (int g = 1; g < p.n_groups; ++g) {
+        // first row r with ptr[r] >= g * nnz / n_groups — the partition rule (spmm_b200_partition_rows)
+        const long long target = (long long)h->num_e * g / p.n_groups;
+        p.group_row[g] = (int)(std::lower_bound(ptr.begin(), ptr.begin() + M, target, [](int a, long long t) { return (long long)a < t; }) - ptr.begin());
+    }
+
+    // ---- host planning of every block (independent of each other) -------------------------------------------------
+    std::vector<HostBlock> hb((size_t)nb);
+#pragma omp parallel for schedule(dynamic, 1) if (nb > 1)
+    for (int b = 0; b < nb; ++b) {
         // passes after the first skip rows without nonzeros in their band — except the last pass, which lists every
         // row: it is the one that delivers final rows (to C, to the stacked-layer targets, to run_host's host buffer)
         const bool skip_empty = b > 0 && b + 1 != nb;
-        int rc = build_block(h, bp, rb, re, skip_empty, stream);
-        if (rc) return rc;
+        plan_block_host(h, row_begin(b), row_end(b), skip_empty, reorder[b], p.n_groups > 1 ? p.group_row.data() : nullptr,
+                        p.n_groups, hb[b]);
     }
+    for (int b = 0; b < nb; ++b)
+        if (hb[b].rc) {
+            set_error("%s", hb[b].err);
+            return hb[b].rc;
+        }
+    tr.lap("host planning (all blocks)");
+
+    // ---- device side: one arena per array kind, band after band ------------------------------------------------------
+    long long lp_total = 0, pn_total = 0, seg_total = 0, heavy_total = 0, task_total = 0;
+    for (int b = 0; b < nb; ++b) {
+        lp_total += hb[b].lpanel_len;
+        pn_total += hb[b].panel_len;
+        seg_total += (long long)hb[b].segs.size();
+        heavy_total += (long long)hb[b].heavy_rows.size();
+        task_total += (long long)hb[b].utask.size();
+    }
+    if (lp_total > 0x7fffffffll || pn_total > 0x7fffffffll || task_total * p.n_slices > 0x7fffffffll) {
+        set_error("plan too large for 32-bit panel offsets (%lld light, %lld heavy entries)", lp_total, pn_total);
+        return SPMM_B200_EINVAL;
+    }
+    if (lp_total) {
+        SB_CUDA(cudaMalloc((void **)&p.d_lpanel_all, sizeof(int2) * (size_t)lp_total));
+        SB_CUDA(cudaMemsetAsync(p.d_lpanel_all, 0xFF, sizeof(int2) * (size_t)lp_total, stream));   // nop entries
+    }
+    if (pn_total) SB_CUDA(cudaMalloc((void **)&p.d_panel_all, sizeof(int2) * (size_t)pn_total));
+    if (seg_total) SB_CUDA(cudaMalloc((void **)&p.d_part_all, sizeof(float) * (size_t)seg_total * K));
+    if (heavy_total) {
+        // n_heavy + 1 slots per band, so that a band's counters sit at its absolute heavy-row base (the persistent
+        // launch addresses them that way, like heavy_seg0)
+        const size_t slots = (size_t)(heavy_total + nb) * p.n_slices;
+        SB_CUDA(cudaMalloc((void **)&p.d_seg_count_all, sizeof(int) * slots));
+        SB_CUDA(cudaMemsetAsync(p.d_seg_count_all, 0, sizeof(int) * slots, stream));
+    }
+    tr.lap("arena allocation");
+    const int groups = p.scalar ? 1 : 32 / p.lanes;
+    const int pad = p.scalar ? 2 : 4 * groups;
+    long long lp_off = 0, pn_off = 0, seg_off = 0, heavy_off = 0;
+    for (int b = 0; b < nb; ++b) {
+        BlockPlan &bp = p.blocks[b];
+        HostBlock &x = hb[b];
+        bp.col_begin = nb > 1 ? b * cols_per_block : 0;
+        bp.col_end = nb > 1 ? (b + 1 == nb ? b_rows : (b + 1) * cols_per_block) : b_rows;
+        bp.reorder = x.reorder;
+        bp.light_steps = x.light_steps;
+        if (b == 0 && h->opt_light_steps <= 0) p.light_steps = x.light_steps;   // reported by plan_info (block 0)
+        bp.n_light = (int)x.row_perm.size();
+        bp.n_heavy = (int)x.heavy_rows.size();
+        bp.n_seg = (int)x.segs.size();
+        bp.panel_len = x.panel_len;
+        bp.lpanel_len = x.lpanel_len;
+        bp.n_ltask = (int)x.ltasks.size();
+        bp.n_utask = (int)x.utask.size();
+        bp.task_group = x.task_group;
+        if ((rc = upload_vec(&bp.d_row_perm, x.row_perm, stream))) return rc;
+        if ((rc = upload_vec(&bp.d_light_desc, x.light, stream))) return rc;
+        if ((rc = upload_vec(&bp.d_utask, x.utask, stream))) return rc;
+        if ((rc = upload_vec(&bp.d_ltask, x.ltasks, stream))) return rc;
+        if (bp.n_ltask > 0) {
+            bp.d_lpanel = p.d_lpanel_all + lp_off;
+            if ((rc = launch_build_lpanel(bp.d_light_desc, bp.n_light, groups, K / 4, h->d_idx, h->d_val, bp.d_lpanel, stream))) return rc;
+        }
+        if (bp.n_heavy > 0) {
+            if ((rc = upload_vec(&bp.d_seg_hrow, x.seg_hrow, stream))) return rc;
+            if ((rc = upload_vec(&bp.d_heavy_rows, x.heavy_rows, stream))) return rc;
+            if ((rc = upload_vec(&bp.d_heavy_seg0, x.heavy_seg0, stream))) return rc;
+            if ((rc = upload_vec(&bp.d_seg_desc, x.segs, stream))) return rc;
+            bp.d_seg_count = p.d_seg_count_all + (heavy_off + b) * p.n_slices;
+            bp.d_panel = p.d_panel_all + pn_off;
+            bp.d_part = p.d_part_all + seg_off * K;
+            if ((rc = launch_build_panel(bp.d_seg_desc, bp.n_seg, K / 4, pad, h->d_idx, h->d_val, bp.d_panel, stream))) return rc;
+        }
+        lp_off += x.lpanel_len;
+        pn_off += x.panel_len;
+        seg_off += (long long)x.segs.size();
+        heavy_off += (long long)x.heavy_rows.size();
+    }
+    tr.lap("uploads + panel kernels queued");
+
+    // ---- the persistent launch's ticket list: band-major, absolute positions, row group and dependency per task ---------
+    std::vector<int4> ptask;
+    std::vector<SegDesc> pseg;
+    std::vector<int> pseg_hrow, pheavy_seg0;
+    if (p.persistent) {
+        ptask.reserve((size_t)task_total);
+        pseg.reserve((size_t)seg_total);
+        pseg_hrow.reserve((size_t)seg_total);
+        pheavy_seg0.reserve((size_t)(heavy_total + nb));
+        std::vector<int> done((size_t)p.n_groups, 0);   // tasks of each group in the bands before the current one
+        long long lp0 = 0, pn0 = 0, seg0 = 0;
+        int hrow0 = 0;   // absolute heavy-row index base: every band contributes n_heavy + 1 entries of heavy_seg0
+        for (int b = 0; b < nb; ++b) {
+            HostBlock &x = hb[b];
+            const int flags = (b > 0 ? 1 << 16 : 0) | (b + 1 == nb ? 1 << 17 : 0);
+            std::vector<int> here((size_t)p.n_groups, 0);
+            for (size_t t = 0; t < x.utask.size(); ++t) {
+                const int2 u = x.utask[t];
+                const int g = x.task_group[t];
+                ++here[g];
+                ptask.push_back(u.x < 0 ? make_int4(-1 - (int)(seg0 + (-1 - u.x)), 0, g | flags, b > 0 ? done[g] : 0)
+                                        : make_int4((int)(lp0 + u.x), u.y, g | flags, b > 0 ? done[g] : 0));
+            }
+            for (int g = 0; g < p.n_groups; ++g) done[g] += here[g];
+            for (size_t sgm = 0; sgm < x.segs.size(); ++sgm) {
+                SegDesc d = x.segs[sgm];
+                d.panel_off += (int)pn0;
+                pseg.push_back(d);
+                pseg_hrow.push_back(hrow0 + x.seg_hrow[sgm]);
+            }
+            for (int v : x.heavy_seg0) pheavy_seg0.push_back((int)seg0 + v);
+            if (x.heavy_seg0.empty()) pheavy_seg0.push_back((int)seg0);   // keep n_heavy + 1 entries per band
+            hrow0 += (int)x.heavy_rows.size() + 1;
+            lp0 += x.lpanel_len;
+            pn0 += x.panel_len;
+            seg0 += (long long)x.segs.size();
+        }
+        p.n_ptask = (int)ptask.size();
+        if ((rc = upload_vec(&p.d_ptask, ptask, stream))) return rc;
+        if ((rc = upload_vec(&p.d_pseg_desc, pseg, stream))) return rc;
+        if ((rc = upload_vec(&p.d_pseg_hrow, pseg_hrow, stream))) return rc;
+        if ((rc = upload_vec(&p.d_pheavy_seg0, pheavy_seg0, stream))) return rc;
+        SB_CUDA(cudaMalloc((void **)&p.d_ctr, sizeof(unsigned int) * (size_t)(2 + p.n_groups)));
+        SB_CUDA(cudaMemsetAsync(p.d_ctr, 0, sizeof(unsigned int) * (size_t)(2 + p.n_groups), stream));
+        p.persist_grid = persistent_grid(p.lanes, p.vec, p.tune, p.block);
+        if (p.persist_grid <= 0) p.persistent = false;   // occupancy could not be queried: one launch per block
+    }
+    SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+    tr.lap("ticket list + final sync");
     p.ready = true;
     return 0;
 }

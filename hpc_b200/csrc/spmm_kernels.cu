@@ -47,18 +47,24 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
 __device__ __forceinline__ void st_c_row(float *p, const float4 &v) {
     __stcs(reinterpret_cast<float4 *>(p), v);
 }
-// A finished C row piece: to vout, and in stacked-layer mode to every rank's copy of the next layer's B —
-// one multimem.st through the NVLS multicast address when there is one, else one st.global per peer-mapped buffer.
-__device__ __forceinline__ void st_final(const RunArgs &a, int row, int col, const float4 &v) {
-    st_c_row(a.cfinal + (size_t)row * a.feat + col, v);
-    if (a.n_gather) {
-        const size_t off = (size_t)(a.gather_row0 + row) * a.feat + col;
-        if (a.gather_mc) {
-            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.gather_mc + off), "f"(v.x),
+// A finished C row piece. Passes that are not the last keep the suspended chain in vout; the final pass stores the
+// row to cfinal (vout, or run_host's pinned host buffer) and, in stacked-layer mode, to every rank's copy of the next
+// layer's B — one multimem.st through the NVLS multicast address when there is one, else one st.global per
+// peer-mapped buffer.
+__device__ __forceinline__ void st_final(const CommonArgs &c, bool final, int row, int col, const float4 &v) {
+    if (!final) {
+        st_c_row(c.vout + (size_t)row * c.feat + col, v);
+        return;
+    }
+    st_c_row(c.cfinal + (size_t)row * c.feat + col, v);
+    if (c.n_gather) {
+        const size_t off = (size_t)(c.gather_row0 + row) * c.feat + col;
+        if (c.gather_mc) {
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c.gather_mc + off), "f"(v.x),
                          "f"(v.y), "f"(v.z), "f"(v.w)
                          : "memory");
         } else {
-            for (int t = 0; t < a.n_gather; ++t) *reinterpret_cast<float4 *>(a.gather[t] + off) = v;
+            for (int t = 0; t < c.n_gather; ++t) *reinterpret_cast<float4 *>(c.gather[t] + off) = v;
         }
     }
 }
@@ -104,9 +110,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 // ---- the SpMM kernel ------------------------------------------------------------------------
 //
-// One launch. Warp tasks are laid out heavy segments first (longest work first), then light
-// rows in plan order; a warp picks its path from its global index, so the tail of the heavy
-// segments overlaps the start of the light rows and nothing waits on a second launch.
+// Warp tasks (equal-sized, TMA-staged spans of a {col,val} panel) are either light-stream tasks or heavy segments, in
+// the order the plan wants them scheduled. Two outer kernels share the task bodies:
+//   spmm_kernel            one launch per column block, one task per warp, scheduled by the hardware (single-block
+//                          plans, and the host-buffer calls, whose passes wait for uploads between launches)
+//   spmm_persistent_kernel ONE launch for all column blocks: a grid of co-resident warps draws tickets from a global
+//                          counter; ticket order is band-major, so the tail of band b overlaps the head of band b+1.
+//                          A task of band b+1 continues chains that band b left in C, so it waits until the tasks of
+//                          band b that own the same ROW GROUP have completed (per-group completion counters; a task
+//                          publishes its completion after its stores are fenced). Waiting is rare — a group's previous
+//                          band ran a whole band earlier — and cannot deadlock: a task only ever waits for smaller
+//                          tickets, which are complete or held by running warps.
 //
 // TUNE selects the gathers kept in flight per lane group and the register cap (option "tune";
 // measurements in profiles/r01_sweep.md):
@@ -123,44 +137,69 @@ struct Tune {
     static constexpr int kUnroll = TUNE == 1 ? 2 : 4;   // gathers in flight per lane group
 };
 
+// A warp's staging pipeline: kStages chunks of shared memory, one mbarrier each. The barriers are (re)initialised at the
+// start of every task, so stage and phase parity follow from the chunk index alone and nothing is carried from task
+// to task in registers.
+struct Pipe {
+    int2 *buf;
+    uint64_t *bars;
+};
+template <bool REUSE>
+__device__ __forceinline__ void pipe_reset(const Pipe &p, int lane) {
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            if (REUSE) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&p.bars[s])) : "memory");
+            mbar_init(&p.bars[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void pipe_issue(const Pipe &p, int k, const int2 *src, uint32_t entries) {
+    const int s = k % kStages;
+    mbar_expect_tx(&p.bars[s], entries * 8u);
+    tma_bulk_g2s(p.buf + s * kChunk, src, entries * 8u, &p.bars[s]);
+}
+__device__ __forceinline__ const int2 *pipe_wait(const Pipe &p, int k) {
+    const int s = k % kStages;
+    mbar_wait(&p.bars[s], (uint32_t)(k / kStages) & 1u);
+    return p.buf + s * kChunk;
+}
+
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
 // Light rows as a stream: a warp walks one task of the light panel, staged through shared
 // memory by 1-D TMA exactly like a heavy segment. Lane group g reads entries g, g+GROUPS, ... of the task:
 // a header starts a new row (the previous row's accumulator is stored first), a nonzero is one B-row gather
 // and one in-order FMA, a nop is padding. Rows never span lane groups, so every row is still one FMA chain in
 // CSR order (bit-exact), but gathers stay in flight across row boundaries and no load depends on a
-// per-row descriptor.
-template <int LANES, int VEC, int TUNE, bool FULL>
-__device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 td, int lane, int2 *buf, uint64_t *bars) {
+// per-row descriptor. `after_issue` runs once the first chunks are on their way (the persistent kernel publishes the
+// previous task and checks this task's dependency there).
+template <int LANES, int VEC, int TUNE, bool FULL, class Hook>
+__device__ __forceinline__ void light_stream(const CommonArgs &c, const BandArgs &bd, bool accumulate, bool final, int slice, int2 td,
+                                             int lane, const Pipe &pipe, Hook &&after_issue) {
     constexpr int GROUPS = 32 / LANES;
     constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
     const int g = lane / LANES;
     const int len = td.y * GROUPS;
     const int nchunks = (len + kChunk - 1) / kChunk;
-    const int2 *src = a.lpanel + td.x;
+    const int2 *src = bd.lpanel + td.x;
 
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        pipe_issue(pipe, 0, src, (uint32_t)min(kChunk, len));   // len is a multiple of 4 * GROUPS
+        if (nchunks > 1) pipe_issue(pipe, 1, src + kChunk, (uint32_t)min(kChunk, len - kChunk));
     }
-    __syncwarp();
-    auto issue = [&](int k) {
-        const int s = k % kStages;
-        const uint32_t bytes = (uint32_t)min(kChunk, len - k * kChunk) * 8u;   // len is even
-        mbar_expect_tx(&bars[s], bytes);
-        tma_bulk_g2s(buf + s * kChunk, src + (size_t)k * kChunk, bytes, &bars[s]);
-    };
-    if (lane == 0) {
-        issue(0);
-        if (nchunks > 1) issue(1);
-    }
+    after_issue();
 
-    const int K = a.feat;
-    const int col0 = slice * a.kslice + l * 4;
-    const int col_end = min(K, (slice + 1) * a.kslice);
+    const int K = c.feat;
+    const int col0 = slice * c.kslice + l * 4;
+    const int col_end = min(K, (slice + 1) * c.kslice);
     // panel entries carry the B row's offset in float4 units (col * K/4), so a gather address is one multiply-add
-    const float4 *bbase = reinterpret_cast<const float4 *>(a.vin + col0);
+    const float4 *bbase = reinterpret_cast<const float4 *>(c.vin + col0);
     float4 acc[VEC];
     bool colok[VEC];
 #pragma unroll
@@ -173,15 +212,14 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 t
         if (cur_row >= 0) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v)
-                if (colok[v]) st_final(a, cur_row, col0 + v * LANES * 4, acc[v]);
+                if (colok[v]) st_final(c, final, cur_row, col0 + v * LANES * 4, acc[v]);
         }
     };
 
     for (int k = 0; k < nchunks; ++k) {
-        const int s = k % kStages;
-        mbar_wait(&bars[s], (uint32_t)(k / kStages) & 1u);
+        const int2 *stage = pipe_wait(pipe, k);
         const int n = min(kChunk, len - k * kChunk);
-        const int2 *ep = buf + s * kChunk + g;   // this lane group's entries: ep[0], ep[GROUPS], ...
+        const int2 *ep = stage + g;   // this lane group's entries: ep[0], ep[GROUPS], ...
         for (int t0 = 0; t0 < n; t0 += GROUPS * U, ep += GROUPS * U) {
             float4 b[U][VEC];
             int2 cv[U];
@@ -218,8 +256,8 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 t
                     } else if (cv[u].x != -1) {
                         flush_row();   // header: the previous row of this lane group is complete
                         cur_row = cv[u].x & 0x7fffffff;
-                        if (a.accumulate) {
-                            const float *crow = a.vout + (size_t)cur_row * K + col0;
+                        if (accumulate) {
+                            const float *crow = c.vout + (size_t)cur_row * K + col0;
 #pragma unroll
                             for (int v = 0; v < VEC; ++v)
                                 if (colok[v]) acc[v] = __ldcg(reinterpret_cast<const float4 *>(crow + v * LANES * 4));
@@ -231,45 +269,36 @@ __device__ __forceinline__ void light_stream(const RunArgs &a, int slice, int2 t
                 }
             }
         }
-        __syncwarp();   // every lane is done reading stage s before it is refilled
-        if (lane == 0 && k + kStages < nchunks) issue(k + kStages);
+        __syncwarp();   // every lane is done reading this stage before it is refilled
+        if (lane == 0 && k + kStages < nchunks)
+            pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, len - (k + kStages) * kChunk));
     }
     flush_row();
 }
 
-template <int LANES, int VEC, int TUNE, bool FULL>
-__device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int seg, int lane, int2 *buf, uint64_t *bars) {
+template <int LANES, int VEC, int TUNE, bool FULL, class Hook>
+__device__ __forceinline__ void heavy_segment(const CommonArgs &c, const BandArgs &bd, bool accumulate, bool final, int slice, int seg,
+                                              int lane, const Pipe &pipe, Hook &&after_issue) {
     constexpr int GROUPS = 32 / LANES;
     constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
     const int g = lane / LANES;
-    const SegDesc d = a.seg_desc[seg];
+    const SegDesc d = bd.seg_desc[seg];
     const int plen = (d.len + 4 * GROUPS - 1) / (4 * GROUPS) * (4 * GROUPS);   // the panel span, padded with nops
     const int nchunks = (plen + kChunk - 1) / kChunk;
-    const int2 *src = a.panel + d.panel_off;
+    const int2 *src = bd.panel + d.panel_off;
 
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        pipe_issue(pipe, 0, src, (uint32_t)min(kChunk, plen));
+        if (nchunks > 1) pipe_issue(pipe, 1, src + kChunk, (uint32_t)min(kChunk, plen - kChunk));
     }
-    __syncwarp();
-    auto issue = [&](int k) {
-        const int s = k % kStages;
-        const uint32_t bytes = (uint32_t)min(kChunk, plen - k * kChunk) * 8u;
-        mbar_expect_tx(&bars[s], bytes);
-        tma_bulk_g2s(buf + s * kChunk, src + (size_t)k * kChunk, bytes, &bars[s]);
-    };
-    if (lane == 0) {
-        issue(0);
-        if (nchunks > 1) issue(1);
-    }
+    after_issue();
 
-    const int K = a.feat;
-    const int col0 = slice * a.kslice + l * 4;
-    const int col_end = min(K, (slice + 1) * a.kslice);
+    const int K = c.feat;
+    const int col0 = slice * c.kslice + l * 4;
+    const int col_end = min(K, (slice + 1) * c.kslice);
     // panel entries carry the B row's offset in float4 units (col * K/4), so a gather address is one multiply-add
-    const float4 *bbase = reinterpret_cast<const float4 *>(a.vin + col0);
+    const float4 *bbase = reinterpret_cast<const float4 *>(c.vin + col0);
     float4 acc[VEC];
     bool colok[VEC];
 #pragma unroll
@@ -279,10 +308,8 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
     }
 
     for (int k = 0; k < nchunks; ++k) {
-        const int s = k % kStages;
-        mbar_wait(&bars[s], (uint32_t)(k / kStages) & 1u);
+        const int2 *e = pipe_wait(pipe, k);
         const int n = min(kChunk, plen - k * kChunk);
-        const int2 *e = buf + s * kChunk;
         for (int t0 = 0; t0 < n; t0 += GROUPS * U) {
             float4 b[U][VEC];
             float wt[U];
@@ -292,10 +319,12 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
                 const int2 cv = e[t0 + u * GROUPS + g];   // in range: the span is padded to whole batches
                 ok[u] = cv.x >= 0;                        // nop entries are {-1, 0}
                 wt[u] = __int_as_float(cv.y);
-                const float4 *brow = bbase + (unsigned)cv.x;
+                // a nop gathers row 0 (always a valid address) and is ignored below: every b[u][v] is defined in every
+                // iteration, which keeps the register allocator from carrying the batch across iterations
+                const float4 *brow = bbase + (ok[u] ? (unsigned)cv.x : 0u);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (ok[u] && colok[v]) b[u][v] = __ldg(brow + v * LANES);
+                    if (colok[v]) b[u][v] = __ldg(brow + v * LANES);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -304,8 +333,9 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
                     if (ok[u] && colok[v]) fma4(acc[v], b[u][v], wt[u]);
             }
         }
-        __syncwarp();   // every lane is done reading stage s before it is refilled
-        if (lane == 0 && k + kStages < nchunks) issue(k + kStages);
+        __syncwarp();   // every lane is done reading this stage before it is refilled
+        if (lane == 0 && k + kStages < nchunks)
+            pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, plen - (k + kStages) * kChunk));
     }
 
     // combine the lane groups (fixed tree => deterministic)
@@ -320,7 +350,7 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
         }
     }
     if (g == 0) {
-        float *prow = a.part + (size_t)seg * K + col0;
+        float *prow = bd.part + (size_t)seg * K + col0;
 #pragma unroll
         for (int v = 0; v < VEC; ++v)
             if (colok[v]) __stcg(reinterpret_cast<float4 *>(prow + v * LANES * 4), acc[v]);
@@ -331,11 +361,11 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
     // Segment reduction without a second launch and without float atomics: the warp that
     // finishes a row's last outstanding segment adds the partials IN SEGMENT ORDER, so the
     // result does not depend on which warp that is. The counter returns to zero for the next run.
-    const int hrow = a.seg_hrow[seg];
-    const int s0 = a.heavy_seg0[hrow], s1 = a.heavy_seg0[hrow + 1];
+    const int hrow = bd.seg_hrow[seg];
+    const int s0 = bd.heavy_seg0[hrow], s1 = bd.heavy_seg0[hrow + 1];
     int last = 0;
     if (lane == 0) {
-        int *cnt = a.seg_count + (size_t)hrow * a.n_slices + slice;
+        int *cnt = bd.seg_count + (size_t)hrow * c.n_slices + slice;
         last = atomicAdd(cnt, 1) == s1 - s0 - 1;
         if (last) *cnt = 0;
     }
@@ -344,10 +374,10 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
     // acquire side, executed by every lane that is about to read the other warps' partials (the writers fenced
     // after their stores and before the counter was bumped)
     __threadfence();
-    float *crow = a.vout + (size_t)d.row * K;
-    for (int col = slice * a.kslice + lane * 4; col < col_end; col += 128) {
-        const float *p = a.part + (size_t)s0 * K + col;
-        float4 sum = a.accumulate ? __ldcg(reinterpret_cast<const float4 *>(crow + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *crow = c.vout + (size_t)d.row * K;
+    for (int col = slice * c.kslice + lane * 4; col < col_end; col += 128) {
+        const float *p = bd.part + (size_t)s0 * K + col;
+        float4 sum = accumulate ? __ldcg(reinterpret_cast<const float4 *>(crow + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int sgm = s0; sgm < s1; ++sgm, p += K) {
             const float4 x = __ldcg(reinterpret_cast<const float4 *>(p));
             sum.x += x.x;
@@ -355,35 +385,120 @@ __device__ __forceinline__ void heavy_segment(const RunArgs &a, int slice, int s
             sum.z += x.z;
             sum.w += x.w;
         }
-        st_final(a, d.row, col, sum);
+        st_final(c, final, d.row, col, sum);
     }
 }
 
 template <int LANES, int VEC, int TUNE, bool FULL>
-__global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_kernel(const RunArgs a) {
+__global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_kernel(const __grid_constant__ RunArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
     const long long gw = (long long)blockIdx.x * nwarps + warp;
-    // one task list per feature slice: {lpanel offset, steps} for a light-stream task, {-1 - segment, 0} for a heavy
-    // segment, in the order the plan wants them scheduled
-    const int slice = (int)(gw / a.n_utask);
-    if (slice >= a.n_slices) return;
-    const int2 td = __ldg(a.utask + (gw - (long long)slice * a.n_utask));
-    int2 *buf = reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk;
-    uint64_t *bars =
-        reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages;
-    if (td.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a, slice, -1 - td.x, lane, buf, bars);
-    else light_stream<LANES, VEC, TUNE, FULL>(a, slice, td, lane, buf, bars);
+    // one task list per feature slice, in the order the plan wants them scheduled
+    const int slice = (int)(gw / a.b.n_utask);
+    if (slice >= a.c.n_slices) return;
+    const int2 td = __ldg(a.b.utask + (gw - (long long)slice * a.b.n_utask));
+    const Pipe pipe = {reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk,
+                       reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages};
+    pipe_reset<false>(pipe, lane);
+    if (td.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a.c, a.b, a.b.accumulate != 0, a.b.final != 0, slice, -1 - td.x, lane, pipe, NoHook());
+    else light_stream<LANES, VEC, TUNE, FULL>(a.c, a.b, a.b.accumulate != 0, a.b.final != 0, slice, td, lane, pipe, NoHook());
+}
+
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// What a persistent warp does once a task's first chunks are on their way: request its next ticket (parked in shared
+// memory while the task runs), publish the completion of its previous task — every lane fences its own stores (C rows,
+// partial rows), then one count for the task's row group — and wait until the tasks of earlier bands that own the same
+// row group have completed. Publishing comes before waiting: the tasks this warp waits for can include its own
+// previous one.
+struct PersistHook {
+    unsigned int *ticket;
+    unsigned int *grp_done;
+    volatile unsigned int *next_slot;
+    int pending;   // row group of the finished, not yet published task, or -1
+    int group;     // this task's row group
+    int need;      // completed tasks of that group this task waits for (0: none)
+    int lane;
+    __device__ __forceinline__ void operator()() const {
+        if (lane == 0) *next_slot = atomicAdd(ticket, 1u);
+        if (pending >= 0) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(grp_done + pending, 1u);
+        }
+        if (need > 0) {
+            if (lane == 0)
+                while ((int)ld_relaxed_gpu(grp_done + group) < need) __nanosleep(32);
+            __syncwarp();
+            __threadfence();   // acquire side for every lane that will read C rows of the earlier band
+        }
+    }
+};
+
+template <int LANES, int VEC, int TUNE, bool FULL>
+__global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_persistent_kernel(const __grid_constant__ PersistArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    unsigned int *const ticket = a.ctr, *const exited = a.ctr + 1, *const grp_done = a.ctr + 2;
+    const Pipe pipe = {reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk,
+                       reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages};
+    // this warp's next ticket, parked in shared memory while a task runs (after the barriers)
+    volatile unsigned int *next_slot =
+        reinterpret_cast<unsigned int *>(smem_raw + (size_t)nwarps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t))) + warp;
+    pipe_reset<false>(pipe, lane);
+
+    int pending = -1;   // row group of the task this warp finished but has not yet published
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    bool first = true;
+    while (t < (unsigned int)a.total) {
+        // {lpanel offset | -1 - segment, steps, row group | accumulate << 16 | final << 17, completions to wait for}
+        const int4 pt = __ldg(a.ptask + t);
+        const bool accumulate = (pt.z >> 16) & 1, final = (pt.z >> 17) & 1;
+        if (!first) pipe_reset<true>(pipe, lane);
+        first = false;
+        const PersistHook hook = {ticket, grp_done, next_slot, pending, pt.z & 0xffff, pt.w, lane};
+        if (pt.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, -1 - pt.x, lane, pipe, hook);
+        else light_stream<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, make_int2(pt.x, pt.y), lane, pipe, hook);
+        pending = final ? -1 : (pt.z & 0xffff);   // nobody waits for the last band
+        __syncwarp();
+        t = *next_slot;
+    }
+    // the last task's completion
+    if (pending >= 0) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(grp_done + pending, 1u);
+    }
+    // the last warp out returns the counters to zero for the next run (nobody is left to read them)
+    if (lane == 0) {
+        const unsigned int total_warps = gridDim.x * nwarps;
+        if (atomicAdd(exited, 1u) == total_warps - 1) {
+            for (int g = 0; g < a.n_groups; ++g) grp_done[g] = 0;
+            *ticket = 0;
+            *exited = 0;
+            __threadfence();
+        }
+    }
 }
 
 // K % 4 != 0: scalar lanes over the feature columns, one warp per row, same in-order chain.
-__global__ void __launch_bounds__(256) spmm_scalar_kernel(const RunArgs a) {
+__global__ void __launch_bounds__(256) spmm_scalar_kernel(const __grid_constant__ RunArgs ra) {
+    const CommonArgs &a = ra.c;
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= a.n_light) return;
-    const int4 d = __ldg(a.light_desc + gw);
+    if (gw >= ra.b.n_light) return;
+    const int4 d = __ldg(ra.b.light_desc + gw);
     const int row = d.x, begin = d.y, deg = d.z;
     const int K = a.feat;
     for (int cb = 0; cb < K; cb += 32) {
@@ -513,37 +628,120 @@ __global__ void __launch_bounds__(256) valid_kernel(const float *y, const float 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
 }
 
+// per warp: kStages chunks + their mbarriers, and one word for the persistent kernel's parked ticket
+size_t task_smem(int block) { return (size_t)(block / 32) * (kStages * (kChunk * sizeof(int2) + sizeof(uint64_t)) + sizeof(unsigned int)); }
+
 template <int LANES, int VEC, int TUNE, bool FULL>
 void launch_tuned(const RunArgs &a, int block, cudaStream_t stream) {
     const int warps = block / 32;
-    const long long tasks = (long long)a.n_utask * a.n_slices;
-    const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
-    spmm_kernel<LANES, VEC, TUNE, FULL><<<(unsigned)((tasks + warps - 1) / warps), block, smem, stream>>>(a);
+    const long long tasks = (long long)a.b.n_utask * a.c.n_slices;
+    spmm_kernel<LANES, VEC, TUNE, FULL><<<(unsigned)((tasks + warps - 1) / warps), block, task_smem(block), stream>>>(a);
+}
+template <int LANES, int VEC, int TUNE, bool FULL>
+void launch_tuned(const PersistArgs &a, int block, int grid, cudaStream_t stream) {
+    spmm_persistent_kernel<LANES, VEC, TUNE, FULL><<<(unsigned)grid, block, task_smem(block), stream>>>(a);
 }
 
-template <int LANES, int VEC>
-void launch_shape(const RunArgs &a, int block, int tune, bool full, cudaStream_t stream) {
+// Args = RunArgs (extra = nothing) or PersistArgs (extra = grid)
+template <int LANES, int VEC, class Args, class... Extra>
+void launch_shape(const Args &a, int block, int tune, bool full, cudaStream_t stream, Extra... extra) {
     if (tune == 1) {
-        if (full) launch_tuned<LANES, VEC, 1, true>(a, block, stream);
-        else launch_tuned<LANES, VEC, 1, false>(a, block, stream);
+        if (full) launch_tuned<LANES, VEC, 1, true>(a, block, extra..., stream);
+        else launch_tuned<LANES, VEC, 1, false>(a, block, extra..., stream);
     } else {
-        if (full) launch_tuned<LANES, VEC, 0, true>(a, block, stream);
-        else launch_tuned<LANES, VEC, 0, false>(a, block, stream);
+        if (full) launch_tuned<LANES, VEC, 0, true>(a, block, extra..., stream);
+        else launch_tuned<LANES, VEC, 0, false>(a, block, extra..., stream);
     }
 }
 
+template <class Args, class... Extra>
+int launch_lanes(const Plan &p, const Args &a, bool full, cudaStream_t stream, Extra... extra) {
+    switch (p.lanes * 10 + p.vec) {
+        case 11: launch_shape<1, 1>(a, p.block, p.tune, full, stream, extra...); break;
+        case 21: launch_shape<2, 1>(a, p.block, p.tune, full, stream, extra...); break;
+        case 41: launch_shape<4, 1>(a, p.block, p.tune, full, stream, extra...); break;
+        case 81: launch_shape<8, 1>(a, p.block, p.tune, full, stream, extra...); break;
+        case 161: launch_shape<16, 1>(a, p.block, p.tune, full, stream, extra...); break;
+        case 321: launch_shape<32, 1>(a, p.block, p.tune, full, stream, extra...); break;
+        case 322: launch_shape<32, 2>(a, p.block, p.tune, full, stream, extra...); break;
+        default:
+            set_error("unsupported kernel shape lanes=%d vec=%d", p.lanes, p.vec);
+            return SPMM_B200_EINVAL;
+    }
+    return 0;
+}
+
 template <int LANES, int VEC>
-int slots_shape(int block, int tune) {
+int slots_shape(int block, int tune, bool persistent) {
     int nb = 0;
-    const int warps = block / 32;
-    const size_t smem = (size_t)warps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t));
-    cudaError_t e = tune == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_kernel<LANES, VEC, 1, true>, block, smem)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_kernel<LANES, VEC, 0, true>, block, smem);
+    const size_t smem = task_smem(block);
+    cudaError_t e;
+    if (persistent)
+        e = tune == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_persistent_kernel<LANES, VEC, 1, true>, block, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_persistent_kernel<LANES, VEC, 0, true>, block, smem);
+    else
+        e = tune == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_kernel<LANES, VEC, 1, true>, block, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_kernel<LANES, VEC, 0, true>, block, smem);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    return nb * warps;
+    return nb;
+}
+
+int ctas_per_sm(int lanes, int vec, int tune, int block, bool persistent) {
+    switch (lanes * 10 + vec) {
+        case 11: return slots_shape<1, 1>(block, tune, persistent);
+        case 21: return slots_shape<2, 1>(block, tune, persistent);
+        case 41: return slots_shape<4, 1>(block, tune, persistent);
+        case 81: return slots_shape<8, 1>(block, tune, persistent);
+        case 161: return slots_shape<16, 1>(block, tune, persistent);
+        case 321: return slots_shape<32, 1>(block, tune, persistent);
+        case 322: return slots_shape<32, 2>(block, tune, persistent);
+        default: return 0;
+    }
+}
+
+int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return sms;
+}
+
+void fill_common(CommonArgs &c, const spmm_b200_handle *h, const float *vin, float *vout, float *cfinal) {
+    const Plan &p = h->plan;
+    c.idx = h->d_idx;
+    c.val = h->d_val;
+    c.vin = vin;
+    c.vout = vout;
+    c.cfinal = cfinal ? cfinal : vout;
+    c.feat = h->feat;
+    c.kslice = p.kslice;
+    c.n_slices = p.n_slices;
+    c.n_gather = h->n_gather;
+    for (int t = 0; t < kMaxGather; ++t) c.gather[t] = h->gather[t];
+    c.gather_mc = h->gather_mc;
+    c.gather_row0 = h->gather_row0;
+}
+
+void fill_band(BandArgs &b, const Plan &p, int blk) {
+    const BlockPlan &bp = p.blocks[blk];
+    b.light_desc = bp.d_light_desc;
+    b.n_light = bp.n_light;
+    b.utask = bp.d_utask;
+    b.n_utask = bp.n_utask;
+    b.lpanel = bp.d_lpanel;
+    b.seg_desc = bp.d_seg_desc;
+    b.seg_hrow = bp.d_seg_hrow;
+    b.heavy_seg0 = bp.d_heavy_seg0;
+    b.seg_count = bp.d_seg_count;
+    b.panel = bp.d_panel;
+    b.part = bp.d_part;
+    b.accumulate = blk > 0;
+    b.final = blk + 1 == p.n_col_blocks;   // only the last pass produces final rows
 }
 
 }  // namespace
@@ -553,54 +751,45 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
     const Plan &p = h->plan;
     *launches = 0;
     if (h->num_v == 0 || h->feat == 0) return 0;
+    const bool full = !p.scalar && h->feat % (p.lanes * p.vec * 4) == 0 && p.kslice == p.lanes * p.vec * 4;
+    // One persistent launch for all column blocks — unless the passes wait for uploads between launches (band_ready:
+    // the host-buffer calls, which PCIe bounds anyway).
+    if (p.persistent && !band_ready) {
+        PersistArgs a;
+        fill_common(a.c, h, vin, vout, cfinal);
+        a.all = BandArgs();
+        a.all.lpanel = p.d_lpanel_all;
+        a.all.panel = p.d_panel_all;
+        a.all.seg_desc = p.d_pseg_desc;
+        a.all.seg_hrow = p.d_pseg_hrow;
+        a.all.heavy_seg0 = p.d_pheavy_seg0;
+        a.all.seg_count = p.d_seg_count_all;
+        a.all.part = p.d_part_all;
+        a.ptask = p.d_ptask;
+        a.total = p.n_ptask;
+        a.ctr = p.d_ctr;
+        a.n_groups = p.n_groups;
+        if (a.total > 0) {
+            int rc = launch_lanes(p, a, full, stream, p.persist_grid);
+            if (rc) return rc;
+            ++*launches;
+        }
+        SB_CUDA(cudaGetLastError());
+        return 0;
+    }
     for (int blk = 0; blk < p.n_col_blocks; ++blk) {
         const BlockPlan &bp = p.blocks[blk];
         if (band_ready) SB_CUDA(cudaStreamWaitEvent(stream, band_ready[blk], 0));
         if (bp.n_light == 0 && bp.n_seg == 0) continue;
         RunArgs a;
-        a.idx = h->d_idx;
-        a.val = h->d_val;
-        a.vin = vin;
-        a.vout = vout;
-        a.feat = h->feat;
-        a.kslice = p.kslice;
-        a.n_slices = p.n_slices;
-        a.light_desc = bp.d_light_desc;
-        a.n_light = bp.n_light;
-        a.utask = bp.d_utask;
-        a.n_utask = bp.n_utask;
-        a.lpanel = bp.d_lpanel;
-        a.seg_desc = bp.d_seg_desc;
-        a.seg_hrow = bp.d_seg_hrow;
-        a.seg_count = bp.d_seg_count;
-        a.panel = bp.d_panel;
-        a.part = bp.d_part;
-        a.n_seg = bp.n_seg;
-        a.heavy_seg0 = bp.d_heavy_seg0;
-        a.accumulate = blk > 0;
-        const bool last = blk + 1 == p.n_col_blocks;   // only the last pass produces final rows
-        a.cfinal = last && cfinal ? cfinal : vout;
-        a.n_gather = last ? h->n_gather : 0;
-        for (int t = 0; t < kMaxGather; ++t) a.gather[t] = h->gather[t];
-        a.gather_mc = h->gather_mc;
-        a.gather_row0 = h->gather_row0;
+        fill_common(a.c, h, vin, vout, cfinal);
+        fill_band(a.b, p, blk);
         if (p.scalar) {
             const int warps = p.block / 32;
-            spmm_scalar_kernel<<<(unsigned)((a.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
+            spmm_scalar_kernel<<<(unsigned)((a.b.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
         } else {
-            const bool full = h->feat % (p.lanes * p.vec * 4) == 0 && p.kslice == p.lanes * p.vec * 4;
-            switch (p.lanes * 10 + p.vec) {
-                case 11: launch_shape<1, 1>(a, p.block, p.tune, full, stream); break;
-                case 21: launch_shape<2, 1>(a, p.block, p.tune, full, stream); break;
-                case 41: launch_shape<4, 1>(a, p.block, p.tune, full, stream); break;
-                case 81: launch_shape<8, 1>(a, p.block, p.tune, full, stream); break;
-                case 161: launch_shape<16, 1>(a, p.block, p.tune, full, stream); break;
-                case 321: launch_shape<32, 1>(a, p.block, p.tune, full, stream); break;
-                case 322: launch_shape<32, 2>(a, p.block, p.tune, full, stream); break;
-                default:
-                    set_error("unsupported kernel shape lanes=%d vec=%d", p.lanes, p.vec);
-                    return SPMM_B200_EINVAL;
-            }
+            int rc = launch_lanes(p, a, full, stream);
+            if (rc) return rc;
         }
         ++*launches;
     }
@@ -610,24 +799,11 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
 
 // warps the device keeps resident for this kernel shape (0 when it cannot be queried, e.g. no device)
 int resident_warps(int lanes, int vec, int tune, int block) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    int per_sm = 0;
-    switch (lanes * 10 + vec) {
-        case 11: per_sm = slots_shape<1, 1>(block, tune); break;
-        case 21: per_sm = slots_shape<2, 1>(block, tune); break;
-        case 41: per_sm = slots_shape<4, 1>(block, tune); break;
-        case 81: per_sm = slots_shape<8, 1>(block, tune); break;
-        case 161: per_sm = slots_shape<16, 1>(block, tune); break;
-        case 321: per_sm = slots_shape<32, 1>(block, tune); break;
-        case 322: per_sm = slots_shape<32, 2>(block, tune); break;
-        default: break;
-    }
-    return per_sm * sms;
+    return ctas_per_sm(lanes, vec, tune, block, false) * (block / 32) * sm_count();
 }
+
+// CTAs of the persistent launch: as many as are co-resident
+int persistent_grid(int lanes, int vec, int tune, int block) { return ctas_per_sm(lanes, vec, tune, block, true) * sm_count(); }
 
 // grid cap for the grid-stride support kernels: 16 CTAs per SM of the current device
 static long long stride_grid_cap() {

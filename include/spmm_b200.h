@@ -51,6 +51,10 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "col_blocks" passes over A, each gathering from one band of B rows that fits the L2
  *               (0 = auto: 1 unless B is larger than the L2 and rows are long); needs ascending
  *               columns inside each row, otherwise falls back to 1
+ *   "persistent" -1 (default) = run() is one persistent launch whenever the plan has several column blocks (a grid of
+ *               co-resident warps draws tasks from a counter; band b+1's tasks wait for band b's tasks of the same row
+ *               group), 1 = also for a single block, 0 = one launch per column block. Needs feat_in <= 256.
+ *   "row_groups" row groups of the persistent launch (0 = auto: 16 in natural row order, else 1; at most 64)
  *   "zero_copy" run_host / run_host_sharded: 1 (default) = when the output buffer is pinned host memory the last pass
  *               stores final rows straight into it (no separate device-to-host copy), 0 = always copy
  *   "tune"      measured kernel variant, 0 (default) or 1, see hpc_b200/csrc/spmm_kernels.cu
@@ -133,6 +137,9 @@ typedef struct {
     int resident_warps; /* warps the device keeps resident for the kernel shape (sizes small graphs' tasks) */
     int n_col_blocks;   /* passes over A, one per band of B rows (1 = the whole matrix at once) */
     int col_begin, col_end; /* band of B rows of the selected column block */
+    int persistent;     /* 1: run() is ONE persistent launch over all column blocks (tickets drawn from a counter) */
+    int n_row_groups;   /* row groups ordering the column-block passes inside that launch (1 = whole bands) */
+    int n_tickets;      /* tasks of the persistent launch (all column blocks) */
 } spmm_b200_plan_info_t;
 
 /* With n_col_blocks > 1 the plan holds one set of arrays per column block; plan_info / plan_copy
@@ -161,6 +168,10 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *   6 seg_hrow   int32[n_seg]       index into heavy_rows of each segment's row
  *   7 split      int32[(n_col_blocks+1)*num_v]  block-major: CSR position where column block b starts
  *                                   in row r (empty when n_col_blocks == 1)
+ *  11 ptask      int32[n_tickets*4]  the persistent launch's ticket list, band-major (not per block): {lpanel offset
+ *                                   over all blocks, or -1 - segment over all blocks; steps; row group | accumulate << 16
+ *                                   | final << 17; completed tasks of that row group the task waits for}
+ *  12 group_row  int32[n_row_groups+1] first row of each row group (row g's bound: first row with ptr >= g*nnz/groups)
  * Returns SPMM_B200_EINVAL when `bytes` is not the exact size. */
 int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);
 

@@ -163,13 +163,15 @@ def auto_reorder(lanes: int, total_cost: int, slots: int) -> bool:
     return not (lanes == 32 and slots > 0 and total_cost >= 8 * slots * 64)
 
 
-def pack_light(cost, groups: int, steps: int):
+def pack_light(cost, groups: int, steps: int, cuts=()):
     """Light-stream packing. cost[i] = nonzeros + 1 of the i-th light row in plan order. A row goes to the
     least-filled lane of the current task (lowest index on ties); when that lane is non-empty and would exceed
-    `steps`, the task is closed first. -> (dst slots, tasks [(offset, steps)], panel length)"""
+    `steps`, the task is closed first. `cuts`: row positions before which an open task is closed (row-group
+    boundaries of the persistent launch). -> (dst slots, tasks [(offset, steps)], panel length)"""
     dst, tasks = [], []
     fill = [0] * groups
     off = 0
+    cuts = set(int(c) for c in cuts)
 
     def close():
         nonlocal off, fill
@@ -178,7 +180,9 @@ def pack_light(cost, groups: int, steps: int):
         off += mx * groups
         fill = [0] * groups
 
-    for c in (int(x) for x in cost):
+    for i, c in enumerate(int(x) for x in cost):
+        if i in cuts and any(fill):
+            close()
         g = fill.index(min(fill))
         if fill[g] > 0 and fill[g] + c > steps:
             close()
@@ -190,10 +194,12 @@ def pack_light(cost, groups: int, steps: int):
     return np.asarray(dst, np.int32), np.asarray(tasks, np.int32).reshape(-1, 2), off
 
 
-def light_stream(plan_dict, idx, val, groups: int, steps: int, k4: int = 1) -> dict:
-    """light_desc with header slots, task list and the stream panel for a plan() result."""
+def light_stream(plan_dict, idx, val, groups: int, steps: int, k4: int = 1, group_row=None) -> dict:
+    """light_desc with header slots, task list and the stream panel for a plan() result. group_row: the row-group
+    bounds of the persistent launch (natural row order): no task spans a bound."""
     ld = plan_dict["light_desc"].copy()
-    dst, tasks, length = pack_light(ld[:, 2].astype(np.int64) + 1, groups, steps)
+    cuts = () if group_row is None else [int(np.searchsorted(ld[:, 0], r, side="left")) for r in group_row[1:-1]]
+    dst, tasks, length = pack_light(ld[:, 2].astype(np.int64) + 1, groups, steps, cuts)
     ld[:, 3] = dst
     panel = np.full((length, 2), -1, np.int32)
     idx = np.asarray(idx, np.int32)
@@ -222,6 +228,31 @@ def unified_tasks(plan_dict, stream_dict, reorder: bool) -> np.ndarray:
     keyed = [(first_row[t[0]], 1, t) for t in light] + [(int(plan_dict["seg_desc"][s][0]), 0, heavy[s]) for s in range(nseg)]
     keyed.sort(key=lambda k: (k[0], k[1]))                     # stable: a row's segments stay in order
     return np.asarray([k[2] for k in keyed], np.int32).reshape(-1, 2)
+
+
+def ticket_list(blocks, group_row) -> np.ndarray:
+    """The persistent launch's ticket list. blocks: per column block (utask, light_desc, seg_desc, lpanel length, panel
+    length) in band order. One int32[4] per task, band-major: {lpanel offset over all blocks | -1 - segment over all
+    blocks, steps, row group | accumulate << 16 | final << 17, tasks of that row group in the earlier bands (the
+    completions the task waits for; 0 in the first band)}. A task's row group is that of the row it starts with."""
+    group_row = np.asarray(group_row, np.int64)
+    ng = len(group_row) - 1
+    out, done = [], [0] * ng
+    lp0 = seg0 = 0
+    nb = len(blocks)
+    for b, (utask, light_desc, seg_desc, lpanel_len, panel_len) in enumerate(blocks):
+        first_row = {int(d): int(r) for r, _, _, d in light_desc}
+        flags = ((1 << 16) if b > 0 else 0) | ((1 << 17) if b + 1 == nb else 0)
+        here = [0] * ng
+        for x, y in utask:
+            row = int(seg_desc[-1 - x][0]) if x < 0 else first_row[int(x)]
+            g = int(np.searchsorted(group_row, row, side="right")) - 1 if ng > 1 else 0
+            here[g] += 1
+            out.append((-1 - (seg0 + (-1 - int(x))) if x < 0 else lp0 + int(x), int(y), g | flags, done[g] if b > 0 else 0))
+        done = [a + c for a, c in zip(done, here)]
+        lp0 += lpanel_len
+        seg0 += len(seg_desc)
+    return np.asarray(out, np.int32).reshape(-1, 4)
 
 
 def student_split_check(ptr, tasks) -> bool:

@@ -420,6 +420,56 @@ def test_column_block_plan_matches_oracle(shape, K, nb, seg_len):
     op.close()
 
 
+@pytest.mark.parametrize("shape,K,nb,seg_len,groups", [("c0", 256, 3, 32, 4), ("arxiv", 256, 4, 0, 16), ("c0", 32, 3, 16, 1),
+                                                       ("c0", 128, 1, 64, 0)])
+def test_persistent_plan_matches_oracle(shape, K, nb, seg_len, groups):
+    """The single persistent launch: row groups, tasks cut at group bounds, band-major ticket list with dependency
+    counts — every array against the numpy restatement (oracle/plan_oracle.py::ticket_list)."""
+    ptr, idx = H.gen_named_graph(shape)
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    natural = groups != 1
+    op = H.SpMMB200(g, K, col_blocks=nb, seg_len=seg_len, reorder=0 if natural else 1, persistent=1, row_groups=groups)
+    op.preprocess(vin, vout)
+    info = op.plan_info(0)
+    assert info["persistent"] == 1 and info["n_col_blocks"] == nb
+    want_groups = (groups or 16) if (natural and nb > 1) else 1
+    assert info["n_row_groups"] == want_groups
+    M = g.num_v
+    val = g.val.cpu().numpy()
+    group_row = P.partition_rows(ptr, want_groups)
+    split = P.split_rows(ptr, idx, nb, M) if nb > 1 else np.stack([ptr[:-1], ptr[1:]])
+    blocks, n_tasks = [], 0
+    for b in range(nb):
+        got = op.plan_arrays(b)
+        inf = op.plan_info(b)
+        if b == 0:
+            assert np.array_equal(got["group_row"], group_row)
+        want = P.plan(ptr, idx, val, inf["seg_len"], not natural, rb=split[b], re=split[b + 1], skip_empty=0 < b < nb - 1, k4=K // 4,
+                      pad=4 * (32 // inf["lanes"]))
+        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"], k4=K // 4,
+                                   group_row=group_row if want_groups > 1 else None))
+        want["utask"] = P.unified_tasks(want, want, not natural)
+        for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel", "utask"):
+            assert np.array_equal(got[k], want[k]), (b, k)
+        blocks.append((want["utask"], want["light_desc"], want["seg_desc"], len(want["lpanel"]), len(want["panel"])))
+        n_tasks += len(want["utask"])
+    tickets = P.ticket_list(blocks, group_row)
+    assert info["n_tickets"] == n_tasks == len(tickets)
+    assert np.array_equal(op.plan_arrays(0)["ptask"], tickets)
+    # no light task spans a row-group bound; dependency counts never exceed the tasks issued before the ticket
+    grp, need = tickets[:, 2] & 0xffff, tickets[:, 3]
+    assert np.all(need <= np.arange(len(tickets)))
+    assert np.all(grp < want_groups)
+    # and it computes the right thing, repeatedly (the counters return to zero after every run)
+    for _ in range(3):
+        vout.fill_(float("nan"))
+        op.run(vin, vout)
+    torch.cuda.synchronize()
+    assert op.launches_per_run == 1
+    check_against_oracle(ptr, idx, K, op, g, vin, vout[: M * K].cpu().numpy().reshape(M, K))
+    op.close()
+
+
 def test_unsorted_columns_fall_back_to_one_block():
     rows = [[(5, 1.0), (1, 2.0), (3, 3.0)], [(2, 1.0)], [], [(0, 1.0), (7, -1.0)]] + [[] for _ in range(4)]
     ptr, idx, val = tiny_csr(rows)
