@@ -63,6 +63,8 @@ SIGNATURES = {
     "spmm_b200_load_graph": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), _P, _P]),
     "spmm_b200_write_graph": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _I]),
     "spmm_b200_partition_rows": (_I, [_P, _I, _I, _P]),
+    "spmm_b200_partition_rows_weighted": (_I, [_P, _I, _I, _I, _P]),
+    "spmm_b200_plan_row_cost": (_I, [_I, _LL, _I, _I]),
     "spmm_b200_rebase_ptr": (_I, [_P, _I, _I, _P]),
     "spmm_b200_set_replicate": (_I, [_P, _I, _I, C.POINTER(_P), _P, C.POINTER(_P)]),
     "spmm_b200_run_host_sharded": (_I, [_P, _P, _P, _P]),

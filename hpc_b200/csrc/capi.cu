@@ -357,6 +357,7 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
             want = pl.n_col_blocks > 1 ? sizeof(int) * (size_t)(pl.n_col_blocks + 1) * h->num_v : 0;
             break;
         case 11: src = pl.d_ptask; want = sizeof(int4) * (size_t)pl.n_ptask; break;
+        case 13: src = pl.d_ctr; want = pl.d_ctr ? sizeof(unsigned int) * (size_t)(2 + pl.n_groups + 8) : 0; break;
         case 12: {
             want = pl.group_row.empty() ? 0 : sizeof(int) * pl.group_row.size();
             if (bytes != want) break;

@@ -434,6 +434,30 @@ extern "C" int spmm_b200_partition_rows(const int *h_ptr, int num_v, int parts, 
     return 0;
 }
 
+// Cost-balanced variant: a row costs its nonzeros plus `row_cost` (the plan's per-row overhead: one header entry per
+// column block, and the C row it reads and writes there). bounds[g] = first row r with ptr[r] + row_cost * r >=
+// g * (nnz + row_cost * num_v) / parts, 64-bit integers; row_cost = 0 is spmm_b200_partition_rows.
+extern "C" int spmm_b200_partition_rows_weighted(const int *h_ptr, int num_v, int parts, int row_cost, int *bounds) {
+    if (!h_ptr || !bounds || num_v < 0 || parts <= 0 || row_cost < 0) {
+        set_error("partition_rows_weighted: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    const long long total = (long long)h_ptr[num_v] + (long long)row_cost * num_v;
+    bounds[0] = 0;
+    for (int g = 1; g < parts; ++g) {
+        const long long target = (long long)g * total / parts;
+        int lo = 0, hi = num_v;   // first r in [0, num_v] with cost(r) >= target; cost is non-decreasing in r
+        while (lo < hi) {
+            const int mid = lo + (hi - lo) / 2;
+            if ((long long)h_ptr[mid] + (long long)row_cost * mid < target) lo = mid + 1;
+            else hi = mid;
+        }
+        bounds[g] = lo < bounds[g - 1] ? bounds[g - 1] : lo;
+    }
+    bounds[parts] = num_v;
+    return 0;
+}
+
 extern "C" int spmm_b200_rebase_ptr(const int *h_ptr, int row_begin, int row_end, int *out_ptr) {
     if (!h_ptr || !out_ptr || row_begin < 0 || row_end < row_begin) {
         set_error("rebase_ptr: bad arguments");

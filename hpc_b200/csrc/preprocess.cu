@@ -374,6 +374,7 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         p.block = (int)h->opt_block;
         p.n_col_blocks = 1;
         p.blocks.resize(1);
+        p.group_row = {0, M};
         p.ready = true;
         return 0;
     }
@@ -618,8 +619,9 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         if ((rc = upload_vec(&p.d_pseg_desc, pseg, stream))) return rc;
         if ((rc = upload_vec(&p.d_pseg_hrow, pseg_hrow, stream))) return rc;
         if ((rc = upload_vec(&p.d_pheavy_seg0, pheavy_seg0, stream))) return rc;
-        SB_CUDA(cudaMalloc((void **)&p.d_ctr, sizeof(unsigned int) * (size_t)(2 + p.n_groups)));
-        SB_CUDA(cudaMemsetAsync(p.d_ctr, 0, sizeof(unsigned int) * (size_t)(2 + p.n_groups), stream));
+        // ticket, exited warps, per-group completions, 8 watchdog words
+        SB_CUDA(cudaMalloc((void **)&p.d_ctr, sizeof(unsigned int) * (size_t)(2 + p.n_groups + 8)));
+        SB_CUDA(cudaMemsetAsync(p.d_ctr, 0, sizeof(unsigned int) * (size_t)(2 + p.n_groups + 8), stream));
         p.persist_grid = persistent_grid(p.lanes, p.vec, p.tune, p.block);
         if (p.persist_grid <= 0) p.persistent = false;   // occupancy could not be queried: one launch per block
     }
@@ -647,6 +649,11 @@ int refresh_panels(spmm_b200_handle *h, cudaStream_t stream) {
 }
 
 }  // namespace spmm_b200
+
+extern "C" int spmm_b200_plan_row_cost(int num_v, long long nnz, int b_rows, int feat_in) {
+    if (num_v <= 0 || feat_in <= 0) return 1;
+    return spmm_b200::auto_col_blocks(b_rows > 0 ? b_rows : num_v, feat_in, nnz, num_v);
+}
 
 // Host-only plan for CPU-side callers and tests (declared in include/spmm_b200.h).
 extern "C" int spmm_b200_plan_host(const int *h_ptr, int num_v, int feat_in, long long seg_len, int reorder, int *row_perm,

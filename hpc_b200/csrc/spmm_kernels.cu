@@ -86,8 +86,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Watchdog of the persistent launch (wd = a.ctr + 2 + n_groups, 8 words, NULL elsewhere): a wait that lasts longer than
+// ~2 s of SM clocks records what it was waiting for — {kind, a, b, c, d} — once, and gives up, so a scheduling bug
+// shows up as a wrong result with a diagnosis instead of a hung GPU. kind 1: staged chunk (TMA), 2: row-group dependency.
+constexpr long long kWatchdogClocks = 4000000000ll;
+__device__ __noinline__ void watchdog_trip(unsigned int *wd, unsigned int kind, unsigned int a, unsigned int b, unsigned int c,
+                                           unsigned int d) {
+    if (atomicCAS(wd, 0u, kind) == 0u) {
+        wd[1] = a;
+        wd[2] = b;
+        wd[3] = c;
+        wd[4] = d;
+        __threadfence();
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *wd = nullptr, unsigned int info = 0) {
     uint32_t done;
+    long long t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -96,6 +111,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        if (!done && wd) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > kWatchdogClocks) {
+                watchdog_trip(wd, 1u, info, parity, blockIdx.x, threadIdx.x);
+                break;
+            }
+        }
     } while (!done);
 }
 // 1-D TMA: global -> shared, completion counted in bytes on the mbarrier.
@@ -137,24 +159,30 @@ struct Tune {
     static constexpr int kUnroll = TUNE == 1 ? 2 : 4;   // gathers in flight per lane group
 };
 
-// A warp's staging pipeline: kStages chunks of shared memory, one mbarrier each. The barriers are (re)initialised at the
-// start of every task, so stage and phase parity follow from the chunk index alone and nothing is carried from task
-// to task in registers.
+// A warp's staging pipeline: kStages chunks of shared memory, one mbarrier each, initialised once per warp. A task
+// waits for chunk k on stage k % kStages with phase parity (k / kStages) & 1 — which assumes both barriers start the
+// task in an even phase. pipe_finish restores that at the end of a task (one plain arrival completes an idle
+// barrier's phase), so the persistent kernel carries nothing from task to task and never re-initialises a barrier.
 struct Pipe {
     int2 *buf;
     uint64_t *bars;
+    unsigned int *wd;   // watchdog words (persistent launch) or NULL
 };
-template <bool REUSE>
-__device__ __forceinline__ void pipe_reset(const Pipe &p, int lane) {
+__device__ __forceinline__ void pipe_init(const Pipe &p, int lane) {
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            if (REUSE) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&p.bars[s])) : "memory");
-            mbar_init(&p.bars[s], 1);
-        }
+        for (int s = 0; s < kStages; ++s) mbar_init(&p.bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+}
+// after the last chunk of a task has been consumed by every lane (the chunk loops end with __syncwarp)
+__device__ __forceinline__ void pipe_finish(const Pipe &p, int nchunks, int lane) {
+    static_assert(kStages == 2, "phase bookkeeping below is written for two stages");
+    if (lane == 0) {
+        if (((nchunks + 1) >> 1) & 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p.bars[0])) : "memory");
+        if ((nchunks >> 1) & 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&p.bars[1])) : "memory");
+    }
 }
 __device__ __forceinline__ void pipe_issue(const Pipe &p, int k, const int2 *src, uint32_t entries) {
     const int s = k % kStages;
@@ -163,7 +191,7 @@ __device__ __forceinline__ void pipe_issue(const Pipe &p, int k, const int2 *src
 }
 __device__ __forceinline__ const int2 *pipe_wait(const Pipe &p, int k) {
     const int s = k % kStages;
-    mbar_wait(&p.bars[s], (uint32_t)(k / kStages) & 1u);
+    mbar_wait(&p.bars[s], (uint32_t)(k / kStages) & 1u, p.wd, (unsigned int)k);
     return p.buf + s * kChunk;
 }
 
@@ -273,6 +301,7 @@ __device__ __forceinline__ void light_stream(const CommonArgs &c, const BandArgs
         if (lane == 0 && k + kStages < nchunks)
             pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, len - (k + kStages) * kChunk));
     }
+    pipe_finish(pipe, nchunks, lane);
     flush_row();
 }
 
@@ -337,6 +366,7 @@ __device__ __forceinline__ void heavy_segment(const CommonArgs &c, const BandArg
         if (lane == 0 && k + kStages < nchunks)
             pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, plen - (k + kStages) * kChunk));
     }
+    pipe_finish(pipe, nchunks, lane);
 
     // combine the lane groups (fixed tree => deterministic)
 #pragma unroll
@@ -401,15 +431,18 @@ __global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_kernel(
     if (slice >= a.c.n_slices) return;
     const int2 td = __ldg(a.b.utask + (gw - (long long)slice * a.b.n_utask));
     const Pipe pipe = {reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk,
-                       reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages};
-    pipe_reset<false>(pipe, lane);
+                       reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages, nullptr};
+    pipe_init(pipe, lane);
     if (td.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a.c, a.b, a.b.accumulate != 0, a.b.final != 0, slice, -1 - td.x, lane, pipe, NoHook());
     else light_stream<LANES, VEC, TUNE, FULL>(a.c, a.b, a.b.accumulate != 0, a.b.final != 0, slice, td, lane, pipe, NoHook());
 }
 
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
+__device__ __forceinline__ void red_release_gpu(unsigned int *p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -426,19 +459,34 @@ struct PersistHook {
     int group;     // this task's row group
     int need;      // completed tasks of that group this task waits for (0: none)
     int lane;
+    unsigned int *wd;
     __device__ __forceinline__ void operator()() const {
-        if (lane == 0) *next_slot = atomicAdd(ticket, 1u);
+        // Ordered so that the three round trips to L2 overlap each other and the TMA copy already under way: the
+        // release (nothing of this lane is outstanding yet, so its fence is cheap), then the ticket request and the
+        // dependency poll together, and only then the results.
         if (pending >= 0) {
-            __threadfence();
+            // one elected lane releases after the warp barrier (the pattern of a grid barrier: barrier, then one
+            // thread's fence + atomic): the barrier orders every lane's stores before the release, which is cumulative
             __syncwarp();
-            if (lane == 0) atomicAdd(grp_done + pending, 1u);
+            if (lane == 0) red_release_gpu(grp_done + pending);
         }
-        if (need > 0) {
-            if (lane == 0)
-                while ((int)ld_relaxed_gpu(grp_done + group) < need) __nanosleep(32);
-            __syncwarp();
-            __threadfence();   // acquire side for every lane that will read C rows of the earlier band
+        if (lane == 0) {
+            const unsigned int next = atomicAdd(ticket, 1u);
+            if (need > 0) {
+                long long t0 = 0;
+                unsigned int seen;
+                while ((int)(seen = ld_acquire_gpu(grp_done + group)) < need) {
+                    __nanosleep(32);
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > kWatchdogClocks) {
+                        watchdog_trip(wd, 2u, (unsigned int)group, (unsigned int)need, seen, blockIdx.x * blockDim.x + threadIdx.x);
+                        break;
+                    }
+                }
+            }
+            *next_slot = next;
         }
+        __syncwarp();   // extends lane 0's acquire to the lanes that read C rows of the earlier band
     }
 };
 
@@ -450,24 +498,22 @@ __global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_persist
     const int nwarps = blockDim.x >> 5;
     unsigned int *const ticket = a.ctr, *const exited = a.ctr + 1, *const grp_done = a.ctr + 2;
     const Pipe pipe = {reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk,
-                       reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages};
+                       reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages,
+                       a.ctr + 2 + a.n_groups};
     // this warp's next ticket, parked in shared memory while a task runs (after the barriers)
     volatile unsigned int *next_slot =
         reinterpret_cast<unsigned int *>(smem_raw + (size_t)nwarps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t))) + warp;
-    pipe_reset<false>(pipe, lane);
+    pipe_init(pipe, lane);
 
     int pending = -1;   // row group of the task this warp finished but has not yet published
     unsigned int t = 0;
     if (lane == 0) t = atomicAdd(ticket, 1u);
     t = __shfl_sync(kFull, t, 0);
-    bool first = true;
     while (t < (unsigned int)a.total) {
         // {lpanel offset | -1 - segment, steps, row group | accumulate << 16 | final << 17, completions to wait for}
         const int4 pt = __ldg(a.ptask + t);
         const bool accumulate = (pt.z >> 16) & 1, final = (pt.z >> 17) & 1;
-        if (!first) pipe_reset<true>(pipe, lane);
-        first = false;
-        const PersistHook hook = {ticket, grp_done, next_slot, pending, pt.z & 0xffff, pt.w, lane};
+        const PersistHook hook = {ticket, grp_done, next_slot, pending, pt.z & 0xffff, pt.w, lane, pipe.wd};
         if (pt.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, -1 - pt.x, lane, pipe, hook);
         else light_stream<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, make_int2(pt.x, pt.y), lane, pipe, hook);
         pending = final ? -1 : (pt.z & 0xffff);   // nobody waits for the last band
@@ -476,9 +522,8 @@ __global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_persist
     }
     // the last task's completion
     if (pending >= 0) {
-        __threadfence();
         __syncwarp();
-        if (lane == 0) atomicAdd(grp_done + pending, 1u);
+        if (lane == 0) red_release_gpu(grp_done + pending);
     }
     // the last warp out returns the counters to zero for the next run (nobody is left to read them)
     if (lane == 0) {

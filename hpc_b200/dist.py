@@ -17,11 +17,11 @@ from .graph import partition_rows, rebase_ptr
 class RowPartition:
     """Contiguous row blocks balanced by nnz: rank g owns rows [bounds[g], bounds[g+1])."""
 
-    def __init__(self, ptr: np.ndarray, world: int):
+    def __init__(self, ptr: np.ndarray, world: int, row_cost: int = 0):
         self.ptr = np.ascontiguousarray(ptr, dtype=np.int32)
         self.world = int(world)
         self.num_v = len(self.ptr) - 1
-        self.bounds = partition_rows(self.ptr, self.world)
+        self.bounds = partition_rows(self.ptr, self.world, row_cost)
 
     def rows(self, rank: int):
         return int(self.bounds[rank]), int(self.bounds[rank + 1])
@@ -55,12 +55,12 @@ class ShardedSpMM:
     its own row block of C; `allgather` assembles the full C on every rank (e.g. as the next
     layer's B)."""
 
-    def __init__(self, ptr, idx, val, feat: int, group=None, device="cuda", op_factory=None, **options):
+    def __init__(self, ptr, idx, val, feat: int, group=None, device="cuda", op_factory=None, row_cost: int = 0, **options):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.feat = int(feat)
-        self.part = RowPartition(ptr, self.world)
+        self.part = RowPartition(ptr, self.world, row_cost)
         self.num_v = self.part.num_v
         self.row_begin, self.row_end = self.part.rows(self.rank)
         e0, e1 = self.part.nnz_range(self.rank)

@@ -59,12 +59,21 @@ def write_graph(datadir: str, dset: str, ptr: np.ndarray, idx: np.ndarray, text:
                                     1 if text else 0))
 
 
-def partition_rows(ptr: np.ndarray, parts: int) -> np.ndarray:
-    """bounds int32[parts+1]: contiguous row blocks balanced by nnz."""
+def partition_rows(ptr: np.ndarray, parts: int, row_cost: int = 0) -> np.ndarray:
+    """bounds int32[parts+1]: contiguous row blocks balanced by nnz, or by nnz + row_cost per row
+    (the plan's per-row overhead; plan_row_cost) when row_cost > 0."""
     ptr = np.ascontiguousarray(ptr, dtype=np.int32)
     bounds = np.empty(parts + 1, dtype=np.int32)
-    check(lib.spmm_b200_partition_rows(_ip(ptr), len(ptr) - 1, parts, _ip(bounds)))
+    if row_cost:
+        check(lib.spmm_b200_partition_rows_weighted(_ip(ptr), len(ptr) - 1, parts, int(row_cost), _ip(bounds)))
+    else:
+        check(lib.spmm_b200_partition_rows(_ip(ptr), len(ptr) - 1, parts, _ip(bounds)))
     return bounds
+
+
+def plan_row_cost(num_v: int, nnz: int, feat: int, b_rows: int = 0) -> int:
+    """Header entries per row of the automatic plan (= its column blocks): the row_cost to partition with."""
+    return int(lib.spmm_b200_plan_row_cost(int(num_v), int(nnz), int(b_rows), int(feat)))
 
 
 def rebase_ptr(ptr: np.ndarray, row_begin: int, row_end: int) -> np.ndarray:

@@ -171,6 +171,9 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *  11 ptask      int32[n_tickets*4]  the persistent launch's ticket list, band-major (not per block): {lpanel offset
  *                                   over all blocks, or -1 - segment over all blocks; steps; row group | accumulate << 16
  *                                   | final << 17; completed tasks of that row group the task waits for}
+ *  13 counters   uint32[2+n_row_groups+8] the persistent launch's counters {ticket, exited warps, completions per row
+ *                                   group} — all zero between runs — and its 8 watchdog words {kind, ...}: non-zero
+ *                                   kind = a wait inside the launch timed out (1 staged chunk, 2 row-group dependency)
  *  12 group_row  int32[n_row_groups+1] first row of each row group (row g's bound: first row with ptr >= g*nnz/groups)
  * Returns SPMM_B200_EINVAL when `bytes` is not the exact size. */
 int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);
@@ -239,6 +242,16 @@ int spmm_b200_write_graph(const char *datadir, const char *dset, int num_v, int 
 /* nnz-balanced contiguous row partition: bounds[g] = first row r with ptr[r] >= g*nnz/parts
  * (64-bit arithmetic), bounds[0] = 0, bounds[parts] = num_v. h_ptr is a host array. */
 int spmm_b200_partition_rows(const int *h_ptr, int num_v, int parts, int *bounds);
+
+/* Cost-balanced variant: a row costs its nonzeros plus row_cost — the plan's per-row overhead (one header entry
+ * per column block, whose C row is read and written there; spmm_b200_plan_row_cost gives the automatic plan's
+ * figure). bounds[g] = first row r with ptr[r] + row_cost*r >= g*(nnz + row_cost*num_v)/parts. row_cost = 0 is
+ * spmm_b200_partition_rows. */
+int spmm_b200_partition_rows_weighted(const int *h_ptr, int num_v, int parts, int row_cost, int *bounds);
+
+/* Column blocks the automatic plan uses for a graph of num_v rows and nnz nonzeros against a B of b_rows x feat_in
+ * (= header entries per row of the staged plan): the row_cost to balance a partition with. */
+int spmm_b200_plan_row_cost(int num_v, long long nnz, int b_rows, int feat_in);
 
 /* Rebase one partition: out_ptr[i] = h_ptr[row_begin + i] - h_ptr[row_begin], i in [0, rows]. */
 int spmm_b200_rebase_ptr(const int *h_ptr, int row_begin, int row_end, int *out_ptr);

@@ -264,10 +264,12 @@ def student_split_check(ptr, tasks) -> bool:
     return bool(np.array_equal(per_row, -(-deg // 256)))
 
 
-def partition_rows(ptr, parts: int) -> np.ndarray:
-    """bounds[g] = first row r with ptr[r] >= g*nnz//parts (SURVEY.md §8e)."""
+def partition_rows(ptr, parts: int, row_cost: int = 0) -> np.ndarray:
+    """bounds[g] = first row r with ptr[r] + row_cost*r >= g*(nnz + row_cost*m)//parts (SURVEY.md §8e; row_cost = 0:
+    balanced by nonzeros alone)."""
     ptr = np.asarray(ptr, np.int64)
     m = len(ptr) - 1
+    ptr = ptr + row_cost * np.arange(m + 1, dtype=np.int64)
     nnz = int(ptr[m])
     b = [0]
     for g in range(1, parts):

@@ -939,3 +939,21 @@ def test_plain_c_example_runs(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert [float(x) for x in r.stdout.split()] == [32, 37, 42, 47, 0, 0, 0, 0, 0, -1, -2, -3]
+
+
+def test_cpp_multi_gpu_example_runs(tmp_path):
+    """examples/multi_gpu.cpp: the spmm_b200_mg_* driver from a C++ host — host-buffer call and two stacked layers (NCCL
+    all-gather-v vs the kernel epilogue), on every visible GPU and with one GPU listed three times."""
+    import subprocess
+    from conftest import ROOT
+    cuda = "/usr/local/cuda"
+    exe = str(tmp_path / "multi_gpu")
+    r = subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(ROOT, "examples", "multi_gpu.cpp"), "-L", os.path.join(ROOT, "hpc_b200"), "-lspmm_b200",
+                        "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "hpc_b200"), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for n in sorted({1, 3, torch.cuda.device_count()}):
+        r = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (n, r.stdout + r.stderr)
+        assert r.stdout.count("ok") == 2, r.stdout

@@ -112,6 +112,15 @@ def test_partition_rows():
         assert nnz.sum() == ptr[-1]
         # balanced to within the heaviest row
         assert nnz.max() - ptr[-1] / parts <= np.diff(ptr).max()
+    # cost-balanced rule: nonzeros + row_cost per row (the plan's per-row overhead), same integer search
+    for name, parts, rc in [("c0", 3, 1), ("arxiv", 8, 5), ("arxiv", 4, 64)]:
+        ptr, _ = H.gen_named_graph(name)
+        b = H.partition_rows(ptr, parts, rc)
+        assert np.array_equal(b, P.partition_rows(ptr, parts, rc))
+        cost = (ptr[b[1:]].astype(np.int64) - ptr[b[:-1]]) + rc * np.diff(b).astype(np.int64)
+        assert cost.max() - (int(ptr[-1]) + rc * (len(ptr) - 1)) / parts <= np.diff(ptr).max() + rc
+    assert H.plan_row_cost(232965, 114615892, 256) == 5 and H.plan_row_cost(2449029, 123718280, 256) == 1
+    assert H.plan_row_cost(169343, 1166243, 32) == 1
     # degenerate: more parts than rows, empty graph
     ptr = np.asarray([0, 5, 5, 9], np.int32)
     assert np.array_equal(H.partition_rows(ptr, 8), P.partition_rows(ptr, 8))
