@@ -514,6 +514,7 @@ def run_b200(args):
             flush.zero_()
         kms.append(op.run_profiled(vin, vout))
     kernel_ms = float(np.mean(kms))
+    n_launch = max(1, op.launches_per_run)   # of the device-resident run (the host-buffer calls below launch per column block)
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -------------
     e2e_steps = max(3, min(args.steps, 10))
@@ -553,7 +554,6 @@ def run_b200(args):
         flops = 2.0 * nnz * k
         peak, peak_src = measured_peaks()
         total_bytes = bytes_min(lm, lnnz, k, b_rows=m)
-        n_launch = max(1, op.launches_per_run)
         ncu, ncu_src = ncu_record(args.workload) if world == 1 else (None, "captures are single-GPU")
         line = {
             "metric": "spmm_gflops", "value": round(flops / ms_per_step / 1e6, 2), "unit": "GFLOP/s",
@@ -563,7 +563,8 @@ def run_b200(args):
             "config": workload_config(args.workload, ptr),
             "run": {
                 "partition": f"rows by nnz over {world} rank(s), B replicated, no collective",
-                "plan": {kk: info[kk] for kk in ("seg_len", "kslice", "n_slices", "lanes", "vec", "n_col_blocks", "n_light", "n_heavy", "n_seg")},
+                "plan": {kk: info[kk] for kk in ("seg_len", "kslice", "n_slices", "lanes", "vec", "n_col_blocks", "n_light", "n_heavy", "n_seg",
+                                                 "persistent", "n_row_groups", "n_tickets")},
                 "preprocess_s": round(prep_s, 4), "per_rank_ms": [round(x, 5) for x in per_rank_ms],
                 "kernel_source_sha16": kernel_source_sha16(),
             },

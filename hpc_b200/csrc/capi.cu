@@ -162,6 +162,9 @@ int spmm_b200_refresh_values(spmm_b200_t h, void *stream) {
         set_error("spmm_b200_refresh_values: preprocess has not been called");
         return SPMM_B200_ESTATE;
     }
+    // a transposed handle first re-gathers its values from the handle it was built from
+    int rc = regather_transposed_values(h, (cudaStream_t)stream);
+    if (rc) return rc;
     return refresh_panels(h, (cudaStream_t)stream);
 }
 
@@ -278,6 +281,10 @@ int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *s
 int spmm_b200_destroy(spmm_b200_t h) {
     if (!h) return 0;
     free_plan(h->plan);
+    cudaFree(h->t_ptr);
+    cudaFree(h->t_idx);
+    cudaFree(h->t_val);
+    cudaFree(h->t_perm);
     cudaFree(h->d_stage_in);
     cudaFree(h->d_stage_out);
     for (cudaEvent_t e : h->band_events) cudaEventDestroy(e);

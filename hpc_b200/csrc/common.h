@@ -168,6 +168,10 @@ struct spmm_b200_handle {
     unsigned int *rep_flags[spmm_b200::kMaxGather] = {nullptr};
     unsigned int rep_epoch = 0;
     long long rep_h2d_bytes = 0;   // host-to-device bytes of the last run_host_sharded call
+    // transposed operator (transpose.cu): the CSR of A^T is owned by this handle; t_src is the handle it was built from
+    int *t_ptr = nullptr, *t_idx = nullptr, *t_perm = nullptr;
+    float *t_val = nullptr;
+    const spmm_b200_handle *t_src = nullptr;
 };
 
 namespace spmm_b200 {
@@ -200,6 +204,9 @@ int launch_fill_normal(float *d_dst, long long n, uint64_t seed, uint64_t stream
                        float stddev, cudaStream_t stream);
 int launch_valid(const float *d_y, const float *d_y2, long long num, unsigned long long *d_count,
                  cudaStream_t stream);
+
+// transpose.cu
+int regather_transposed_values(spmm_b200_handle *t, cudaStream_t stream);
 
 // replicate.cu
 // Push `count` floats at src (16-byte aligned, count % 4 == 0) to the same offset `off` of every buffer in targets[0..n)

@@ -196,7 +196,8 @@ __device__ __forceinline__ const int2 *pipe_wait(const Pipe &p, int k) {
 }
 
 struct NoHook {
-    __device__ __forceinline__ void operator()() const {}
+    __device__ __forceinline__ void start() const {}
+    __device__ __forceinline__ void late() const {}
 };
 
 // Light rows as a stream: a warp walks one task of the light panel, staged through shared
@@ -204,11 +205,11 @@ struct NoHook {
 // a header starts a new row (the previous row's accumulator is stored first), a nonzero is one B-row gather
 // and one in-order FMA, a nop is padding. Rows never span lane groups, so every row is still one FMA chain in
 // CSR order (bit-exact), but gathers stay in flight across row boundaries and no load depends on a
-// per-row descriptor. `after_issue` runs once the first chunks are on their way (the persistent kernel publishes the
+// per-row descriptor. `hook.start()` runs once the first chunks are on their way (the persistent kernel publishes the
 // previous task and checks this task's dependency there).
 template <int LANES, int VEC, int TUNE, bool FULL, class Hook>
 __device__ __forceinline__ void light_stream(const CommonArgs &c, const BandArgs &bd, bool accumulate, bool final, int slice, int2 td,
-                                             int lane, const Pipe &pipe, Hook &&after_issue) {
+                                             int lane, const Pipe &pipe, Hook &&hook) {
     constexpr int GROUPS = 32 / LANES;
     constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
@@ -221,7 +222,7 @@ __device__ __forceinline__ void light_stream(const CommonArgs &c, const BandArgs
         pipe_issue(pipe, 0, src, (uint32_t)min(kChunk, len));   // len is a multiple of 4 * GROUPS
         if (nchunks > 1) pipe_issue(pipe, 1, src + kChunk, (uint32_t)min(kChunk, len - kChunk));
     }
-    after_issue();
+    hook.start();
 
     const int K = c.feat;
     const int col0 = slice * c.kslice + l * 4;
@@ -302,12 +303,13 @@ __device__ __forceinline__ void light_stream(const CommonArgs &c, const BandArgs
             pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, len - (k + kStages) * kChunk));
     }
     pipe_finish(pipe, nchunks, lane);
+    hook.late();
     flush_row();
 }
 
 template <int LANES, int VEC, int TUNE, bool FULL, class Hook>
 __device__ __forceinline__ void heavy_segment(const CommonArgs &c, const BandArgs &bd, bool accumulate, bool final, int slice, int seg,
-                                              int lane, const Pipe &pipe, Hook &&after_issue) {
+                                              int lane, const Pipe &pipe, Hook &&hook) {
     constexpr int GROUPS = 32 / LANES;
     constexpr int U = Tune<TUNE, VEC>::kUnroll;
     const int l = lane % LANES;
@@ -321,7 +323,7 @@ __device__ __forceinline__ void heavy_segment(const CommonArgs &c, const BandArg
         pipe_issue(pipe, 0, src, (uint32_t)min(kChunk, plen));
         if (nchunks > 1) pipe_issue(pipe, 1, src + kChunk, (uint32_t)min(kChunk, plen - kChunk));
     }
-    after_issue();
+    hook.start();
 
     const int K = c.feat;
     const int col0 = slice * c.kslice + l * 4;
@@ -367,6 +369,7 @@ __device__ __forceinline__ void heavy_segment(const CommonArgs &c, const BandArg
             pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, plen - (k + kStages) * kChunk));
     }
     pipe_finish(pipe, nchunks, lane);
+    hook.late();
 
     // combine the lane groups (fixed tree => deterministic)
 #pragma unroll
@@ -446,47 +449,56 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
     return v;
 }
 
-// What a persistent warp does once a task's first chunks are on their way: request its next ticket (parked in shared
-// memory while the task runs), publish the completion of its previous task — every lane fences its own stores (C rows,
-// partial rows), then one count for the task's row group — and wait until the tasks of earlier bands that own the same
-// row group have completed. Publishing comes before waiting: the tasks this warp waits for can include its own
-// previous one.
+// The persistent warp's bookkeeping around a task.
+//   start()  once the task's first chunks are on their way: request the next ticket (parked in shared memory while the
+//            task runs) and check the dependency — the tasks of earlier bands that own the same row group must have
+//            completed. The two round trips to L2 overlap each other and the TMA copy already under way.
+//   late()   right before the task's final stores: publish the completion of the PREVIOUS task (one release-add to its
+//            row group's counter). That late, the previous task's stores were acknowledged long ago, so the release
+//            does not stall; issued at the start of the task it would wait for the row the warp has just flushed.
+// A warp that has to block in start() publishes first: the tasks it waits for can include its own previous one.
+// Lane 0 does the counting; the warp barriers at the end of every chunk and of every task order all lanes' stores
+// before lane 0's release and extend its acquire to them (the pattern of a grid barrier).
 struct PersistHook {
     unsigned int *ticket;
     unsigned int *grp_done;
-    volatile unsigned int *next_slot;
-    int pending;   // row group of the finished, not yet published task, or -1
-    int group;     // this task's row group
-    int need;      // completed tasks of that group this task waits for (0: none)
+    volatile unsigned int *slot;   // [0] next ticket, [1] row group of the finished, unpublished task + 1 (0: none)
+    int flags;                     // this task: row group | accumulate << 16 | final << 17
+    int need;                      // completed tasks of that group this task waits for (0: none)
     int lane;
     unsigned int *wd;
-    __device__ __forceinline__ void operator()() const {
-        // Ordered so that the three round trips to L2 overlap each other and the TMA copy already under way: the
-        // release (nothing of this lane is outstanding yet, so its fence is cheap), then the ticket request and the
-        // dependency poll together, and only then the results.
-        if (pending >= 0) {
-            // one elected lane releases after the warp barrier (the pattern of a grid barrier: barrier, then one
-            // thread's fence + atomic): the barrier orders every lane's stores before the release, which is cumulative
-            __syncwarp();
-            if (lane == 0) red_release_gpu(grp_done + pending);
-        }
+    __device__ __forceinline__ void start() const {
         if (lane == 0) {
             const unsigned int next = atomicAdd(ticket, 1u);
             if (need > 0) {
-                long long t0 = 0;
-                unsigned int seen;
-                while ((int)(seen = ld_acquire_gpu(grp_done + group)) < need) {
-                    __nanosleep(32);
-                    if (t0 == 0) t0 = clock64();
-                    else if (clock64() - t0 > kWatchdogClocks) {
-                        watchdog_trip(wd, 2u, (unsigned int)group, (unsigned int)need, seen, blockIdx.x * blockDim.x + threadIdx.x);
-                        break;
+                const unsigned int *cnt = grp_done + (flags & 0xffff);
+                unsigned int seen = ld_acquire_gpu(cnt);
+                if ((int)seen < need) {
+                    const unsigned int p = slot[1];
+                    if (p) {
+                        red_release_gpu(grp_done + (p - 1));
+                        slot[1] = 0;
+                    }
+                    const long long t0 = clock64();
+                    while ((int)(seen = ld_acquire_gpu(cnt)) < need) {
+                        __nanosleep(32);
+                        if (clock64() - t0 > kWatchdogClocks) {
+                            watchdog_trip(wd, 2u, (unsigned int)(flags & 0xffff), (unsigned int)need, seen, blockIdx.x * blockDim.x + threadIdx.x);
+                            break;
+                        }
                     }
                 }
             }
-            *next_slot = next;
+            slot[0] = next;
         }
         __syncwarp();   // extends lane 0's acquire to the lanes that read C rows of the earlier band
+    }
+    __device__ __forceinline__ void late() const {
+        if (lane == 0) {
+            const unsigned int p = slot[1];
+            if (p) red_release_gpu(grp_done + (p - 1));
+            slot[1] = ((flags >> 17) & 1) ? 0u : (unsigned int)(flags & 0xffff) + 1u;   // nobody waits for the last band
+        }
     }
 };
 
@@ -500,31 +512,28 @@ __global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_persist
     const Pipe pipe = {reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk,
                        reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages,
                        a.ctr + 2 + a.n_groups};
-    // this warp's next ticket, parked in shared memory while a task runs (after the barriers)
-    volatile unsigned int *next_slot =
-        reinterpret_cast<unsigned int *>(smem_raw + (size_t)nwarps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t))) + warp;
+    // two words of shared memory per warp (after the barriers): its next ticket, and its unpublished completion
+    volatile unsigned int *slot =
+        reinterpret_cast<unsigned int *>(smem_raw + (size_t)nwarps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t))) + 2 * warp;
     pipe_init(pipe, lane);
-
-    int pending = -1;   // row group of the task this warp finished but has not yet published
     unsigned int t = 0;
-    if (lane == 0) t = atomicAdd(ticket, 1u);
+    if (lane == 0) {
+        t = atomicAdd(ticket, 1u);
+        slot[1] = 0;
+    }
     t = __shfl_sync(kFull, t, 0);
     while (t < (unsigned int)a.total) {
         // {lpanel offset | -1 - segment, steps, row group | accumulate << 16 | final << 17, completions to wait for}
         const int4 pt = __ldg(a.ptask + t);
         const bool accumulate = (pt.z >> 16) & 1, final = (pt.z >> 17) & 1;
-        const PersistHook hook = {ticket, grp_done, next_slot, pending, pt.z & 0xffff, pt.w, lane, pipe.wd};
+        const PersistHook hook = {ticket, grp_done, slot, pt.z, pt.w, lane, pipe.wd};
         if (pt.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, -1 - pt.x, lane, pipe, hook);
         else light_stream<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, make_int2(pt.x, pt.y), lane, pipe, hook);
-        pending = final ? -1 : (pt.z & 0xffff);   // nobody waits for the last band
-        __syncwarp();
-        t = *next_slot;
+        __syncwarp();   // every lane's stores of this task precede whatever lane 0 releases next
+        t = slot[0];
     }
     // the last task's completion
-    if (pending >= 0) {
-        __syncwarp();
-        if (lane == 0) red_release_gpu(grp_done + pending);
-    }
+    if (lane == 0 && slot[1]) red_release_gpu(grp_done + (slot[1] - 1));
     // the last warp out returns the counters to zero for the next run (nobody is left to read them)
     if (lane == 0) {
         const unsigned int total_warps = gridDim.x * nwarps;
@@ -673,8 +682,8 @@ __global__ void __launch_bounds__(256) valid_kernel(const float *y, const float 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
 }
 
-// per warp: kStages chunks + their mbarriers, and one word for the persistent kernel's parked ticket
-size_t task_smem(int block) { return (size_t)(block / 32) * (kStages * (kChunk * sizeof(int2) + sizeof(uint64_t)) + sizeof(unsigned int)); }
+// per warp: kStages chunks + their mbarriers, and two words for the persistent kernel (parked ticket, unpublished completion)
+size_t task_smem(int block) { return (size_t)(block / 32) * (kStages * (kChunk * sizeof(int2) + sizeof(uint64_t)) + 2 * sizeof(unsigned int)); }
 
 template <int LANES, int VEC, int TUNE, bool FULL>
 void launch_tuned(const RunArgs &a, int block, cudaStream_t stream) {

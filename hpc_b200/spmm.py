@@ -103,6 +103,22 @@ class SpMMB200(SpMM):
         self._check_io(vin, vout)
         check(lib.spmm_b200_preprocess(self._h, _ptr(vin), _ptr(vout), _stream()))
 
+    def transposed(self, feat_in: int | None = None, **options) -> "SpMMB200":
+        """The operator over A^T (spmm_b200_create_transposed): run(dC[num_v x K], dB[b_rows x K]) computes the gradient
+        of this operator with respect to its input. The new operator owns its CSR; close it before this one."""
+        t = object.__new__(SpMMB200)
+        t.g = None
+        t.num_e = self.num_e
+        t.num_v, t.b_rows = self.b_rows, self.num_v
+        t.feat_in = self.feat_in if feat_in is None else int(feat_in)
+        h = C.c_void_p()
+        check(lib.spmm_b200_create_transposed(self._h, t.feat_in, _stream(), C.byref(h)))
+        t._h = h
+        t._parent = self   # keeps the source operator (and the arrays it borrows) alive
+        for k, v in options.items():
+            t.set_option(k, v)
+        return t
+
     def refresh_values(self) -> None:
         """Re-stage the plan's copy of idx/val after the caller changed them in place (same ptr)."""
         check(lib.spmm_b200_refresh_values(self._h, _stream()))

@@ -99,6 +99,14 @@ int spmm_b200_run_profiled(spmm_b200_t h, const float *vin, float *vout, void *s
  * b_rows * feat_in floats; n_targets <= 16; 0 switches the mode off. */
 int spmm_b200_set_gather(spmm_b200_t h, int n_targets, float *const *targets, float *multicast, long long row_offset);
 
+/* The transposed operator (no reference counterpart — PA4 is forward only): a new handle over A^T,
+ * built on the device from h's CSR, for the gradient dB = A^T * dC through the same plan and kernels. Inside a row of
+ * A^T (a column of A) the nonzeros keep A's storage order (ascending row), so every output element is one in-order
+ * FMA chain. The new handle OWNS its CSR arrays; its num_v = h's b_rows (rows of B), its b_rows = h's num_v, so
+ * run(out, dC[num_v x feat_in], dB[b_rows x feat_in]). Use it like any handle (set_option, preprocess, run, destroy);
+ * destroy it before h. spmm_b200_refresh_values on it re-reads h's current values. Synchronises `stream`. */
+int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *stream, spmm_b200_t *out);
+
 /* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). */
 int spmm_b200_destroy(spmm_b200_t h);
 

@@ -29,6 +29,8 @@ def _load():
     lib.oracle_spmm_literal.restype = None
     lib.oracle_spmm_f32.argtypes = [P, P, P, P, P, I, I, I, I, I]
     lib.oracle_spmm_f32.restype = None
+    lib.oracle_spmm_t_f32.argtypes = [P, P, P, P, P, P, I, I, I, I]
+    lib.oracle_spmm_t_f32.restype = None
     lib.oracle_spmm_f64.argtypes = [P, P, P, P, P, I, I, I, I]
     lib.oracle_spmm_f64.restype = None
     lib.oracle_spmm_abssum.argtypes = [P, P, P, P, P, I, I, I]
@@ -76,6 +78,19 @@ def spmm_f32(ptr, idx, val, vin, feat, row_begin=0, row_end=None, ftz=False, nth
         out = np.zeros(m * feat, np.float32)
     _lib.oracle_spmm_f32(_p(ptr), _p(idx), _p(val), _p(vin), _p(out), feat, row_begin, row_end, int(ftz), nthreads)
     return out.reshape(m, feat)
+
+
+def spmm_t_f32(ptr, idx, val, dc, feat, b_rows=None, ftz=False, with_abs=False):
+    """dB = A^T dC: one in-order FMA chain per output element over its column's nonzeros in CSR storage order
+    (no reference counterpart: parity unpinned). -> dB[b_rows, feat] (and the fp64 sum of |terms| with with_abs)."""
+    ptr, idx, val, dc = _csr(ptr, idx, val, dc)
+    m = len(ptr) - 1
+    b_rows = m if b_rows is None else b_rows
+    out = np.empty(b_rows * feat, np.float32)
+    ab = np.empty(b_rows * feat, np.float64) if with_abs else None
+    _lib.oracle_spmm_t_f32(_p(ptr), _p(idx), _p(val), _p(dc), _p(out), _p(ab) if with_abs else None, m, b_rows, feat, int(ftz))
+    out = out.reshape(b_rows, feat)
+    return (out, ab.reshape(b_rows, feat)) if with_abs else out
 
 
 def spmm_f64(ptr, idx, val, vin, feat):

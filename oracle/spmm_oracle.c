@@ -92,6 +92,36 @@ void oracle_spmm_f32(const int *ptr, const int *idx, const float *val, const flo
     }
 }
 
+/*
+ * Transposed product dB = A^T * dC (the gradient of spmm_ref.cu:3-17 with respect to vin; the reference itself has no
+ * backward pass — SURVEY.md 8f-3 — so parity here is UNPINNED: product vs this restatement). Every nonzero
+ * (r, c = idx[i], v = val[i]) contributes dC[r, :] * v to dB[c, :]; walking the CSR in storage order makes each output
+ * element one in-order FMA chain from 0.0f over its column's nonzeros by ascending row (and position), the order the
+ * engine's transposed CSR keeps. Also writes the fp64 sum of |terms| when abs_out is non-NULL (tolerance scale).
+ */
+void oracle_spmm_t_f32(const int *ptr, const int *idx, const float *val, const float *dc, float *db, double *abs_out,
+                       int num_v, int b_rows, int feat, int ftz) {
+    for (size_t t = 0; t < (size_t)b_rows * feat; ++t) db[t] = 0.0f;
+    if (abs_out)
+        for (size_t t = 0; t < (size_t)b_rows * feat; ++t) abs_out[t] = 0.0;
+    for (int r = 0; r < num_v; ++r) {
+        const float *src = dc + (size_t)r * feat;
+        for (int i = ptr[r]; i < ptr[r + 1]; ++i) {
+            const float v = val[i];
+            float *dst = db + (size_t)idx[i] * feat;
+            if (ftz) {
+                for (int j = 0; j < feat; ++j) dst[j] = ffma_ftz(src[j], v, dst[j]);
+            } else {
+                for (int j = 0; j < feat; ++j) dst[j] = fmaf(src[j], v, dst[j]);
+            }
+            if (abs_out) {
+                double *a = abs_out + (size_t)idx[i] * feat;
+                for (int j = 0; j < feat; ++j) a[j] += fabs((double)src[j]) * fabs((double)v);
+            }
+        }
+    }
+}
+
 /* fp64 accumulation of the same sum (error budgeting only; no reference counterpart). */
 void oracle_spmm_f64(const int *ptr, const int *idx, const float *val, const float *vin,
                      double *vout, int feat, int row_begin, int row_end, int nthreads) {

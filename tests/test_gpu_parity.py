@@ -351,7 +351,8 @@ def test_run_host_matches_device_run(opts):
         h_out.fill_(float("nan"))
         op.run_host(h_in, h_out)
         assert np.array_equal(h_out.numpy().view(np.int32), got.ravel().view(np.int32))
-    assert op.run_profiled(vin, vout) > 0 and op.launches_per_run == op.plan_info()["n_col_blocks"]
+    info = op.plan_info()
+    assert op.run_profiled(vin, vout) > 0 and op.launches_per_run == (1 if info["persistent"] else info["n_col_blocks"])
     op.close()
 
 
@@ -703,6 +704,75 @@ def test_feat_zero_is_a_no_op():
     torch.cuda.synchronize()
     check_against_oracle(ptr, idx, 4, op, g, vin, vout[: g.num_v * 4].cpu().numpy().reshape(-1, 4))
     op.close()
+
+
+# ---- the transposed operator: dB = A^T dC (no reference counterpart, parity unpinned) ---------
+
+@pytest.mark.parametrize("shape,K,opts", [("c0", 32, {}), ("c0", 256, {"seg_len": 32}), ("arxiv", 256, {}), ("arxiv", 32, {}),
+                                           ("c0", 33, {}), ("c0", 64, {"col_blocks": 3, "persistent": 1})])
+def test_transposed_operator_matches_oracle(shape, K, opts):
+    ptr, idx = H.gen_named_graph(shape)
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    M = g.num_v
+    fwd = H.SpMMB200(g, K)
+    bwd = fwd.transposed(**opts)
+    dc = H.fill_normal(torch.empty(M * K, device=DEV), 77, 3)
+    db = torch.full((M * K,), float("nan"), device=DEV)
+    bwd.preprocess(dc, db)
+    bwd.run(dc, db)
+    torch.cuda.synchronize()
+    got = db.cpu().numpy().reshape(M, K)
+    want, ab = O.spmm_t_f32(ptr, idx, g.val.cpu().numpy(), dc.cpu().numpy(), K, with_abs=True)
+    heavy = bwd.heavy_row_set()
+    whole = np.asarray([r for r in range(M) if r not in heavy], np.int64)
+    assert np.array_equal(got[whole].view(np.int32), want[whole].view(np.int32)), "whole rows of A^T must be bit-exact"
+    assert np.all(np.abs(got.astype(np.float64) - want) <= TOL * ab + 1e-30)
+    # adjoint identity in fp64: <A x, y> == <x, A^T y>
+    fwd.preprocess(vin, vout)
+    fwd.run(vin, vout)
+    lhs = float((vout[: M * K].double() * dc.double()).sum())
+    rhs = float((vin[: M * K].double() * db.double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * float((vout[: M * K].double().abs() * dc.double().abs()).sum())
+    # edge re-weighting: the transposed operator re-reads the source operator's values
+    g.val.mul_(0.5)
+    bwd.refresh_values()
+    bwd.run(dc, db)
+    torch.cuda.synchronize()
+    assert np.array_equal(db.cpu().numpy().reshape(M, K)[whole].view(np.int32), (want[whole] * np.float32(0.5)).view(np.int32))
+    bwd.close()
+    fwd.close()
+
+
+def test_transposed_operator_of_a_row_block():
+    """A row block of a larger graph (b_rows > num_v): A^T has b_rows rows and gathers from the block's rows of dC."""
+    ptr, idx = H.gen_named_graph("c0")
+    K, M = 32, len(ptr) - 1
+    bounds = H.partition_rows(ptr, 3)
+    val = O.fill_normal(len(idx), 123, 1)
+    total = np.zeros((M, K), np.float64)
+    dc_full = O.fill_normal(M * K, 9, 4).reshape(M, K)
+    for part in range(3):
+        r0, r1 = int(bounds[part]), int(bounds[part + 1])
+        lptr = H.rebase_ptr(ptr, r0, r1)
+        e0, e1 = int(ptr[r0]), int(ptr[r1])
+        g, _, _ = dev_inputs(lptr, idx[e0:e1], K, val=val[e0:e1], b_rows=M)
+        fwd = H.SpMMB200(g, K, b_rows=M)
+        bwd = fwd.transposed()
+        assert (bwd.num_v, bwd.b_rows) == (M, r1 - r0)
+        dc = torch.from_numpy(dc_full[r0:r1].ravel().copy()).to(DEV)
+        db = torch.empty(M * K, device=DEV)
+        bwd.preprocess(dc, db)
+        bwd.run(dc, db)
+        torch.cuda.synchronize()
+        want = O.spmm_t_f32(lptr, idx[e0:e1], val[e0:e1], dc_full[r0:r1].ravel(), K, b_rows=M)
+        heavy = bwd.heavy_row_set()
+        whole = np.asarray([r for r in range(M) if r not in heavy], np.int64)
+        assert np.array_equal(db.cpu().numpy().reshape(M, K)[whole].view(np.int32), want[whole].view(np.int32))
+        total += db.cpu().numpy().reshape(M, K)
+        bwd.close()
+        fwd.close()
+    full = O.spmm_t_f32(ptr, idx, val, dc_full.ravel(), K)
+    assert np.allclose(total, full, rtol=1e-4, atol=1e-5)     # the blocks' gradients add up to the whole graph's
 
 
 # ---- multi-GPU driver behind the C ABI (spmm_b200_mg_*) -----------------------------------------------------

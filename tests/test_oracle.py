@@ -124,3 +124,22 @@ def test_golden_vectors(golden_dir):
         b = O.fill_normal((len(ptr) - 1) * case["K"], case["seed"], 2)
         out = O.spmm_f32(ptr, idx, val, b, case["K"])
         assert np.array_equal(out.view(np.int32), data[f"{n}_out"].view(np.int32).reshape(out.shape)), n
+
+
+def test_transposed_product_oracle_is_the_forward_oracle_on_the_transposed_csr():
+    """oracle_spmm_t_f32 (dB = A^T dC, chains in CSR storage order) == the forward restatement run on A^T built by
+    scipy with each row's entries by ascending row of A — bitwise; and the fp64 abs-sum agrees."""
+    import scipy.sparse as sp
+    import hpc_b200 as H
+    ptr, idx = H.gen_named_graph("c0")
+    M, nnz, K = len(ptr) - 1, len(idx), 8
+    val = O.fill_normal(nnz, 5, 1)
+    dc = O.fill_normal(M * K, 5, 2)
+    got, ab = O.spmm_t_f32(ptr, idx, val, dc, K, with_abs=True)
+    # A^T with explicit positions so that values follow the permutation exactly
+    at = sp.csr_matrix((np.arange(1, nnz + 1, dtype=np.float64), idx, ptr), shape=(M, M)).T.tocsr()
+    at.sort_indices()
+    perm = at.data.astype(np.int64) - 1
+    want = O.spmm_f32(at.indptr.astype(np.int32), at.indices.astype(np.int32), val[perm], dc, K)
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    assert np.allclose(ab, O.spmm_abssum(at.indptr.astype(np.int32), at.indices.astype(np.int32), val[perm], dc, K), rtol=1e-12)
