@@ -83,6 +83,7 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     else if (!strcmp(name, "col_blocks") && value >= 0 && value <= 64) h->opt_col_blocks = value;
     else if (!strcmp(name, "persistent") && value >= -1 && value <= 1) h->opt_persistent = value;
     else if (!strcmp(name, "row_groups") && value >= 0 && value <= kMaxRowGroups) h->opt_row_groups = value;
+    else if (!strcmp(name, "ticket_batch") && value >= 0 && value <= 16) h->opt_ticket_batch = value;
     else if (!strcmp(name, "zero_copy") && value >= 0 && value <= 1) {
         h->opt_zero_copy = value;   // run_host only; not part of the plan
         return 0;
@@ -364,7 +365,7 @@ int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes) 
             want = pl.n_col_blocks > 1 ? sizeof(int) * (size_t)(pl.n_col_blocks + 1) * h->num_v : 0;
             break;
         case 11: src = pl.d_ptask; want = sizeof(int4) * (size_t)pl.n_ptask; break;
-        case 13: src = pl.d_ctr; want = pl.d_ctr ? sizeof(unsigned int) * (size_t)(2 + pl.n_groups + 8) : 0; break;
+        case 13: src = pl.d_ctr; want = pl.d_ctr ? sizeof(unsigned int) * ctr_words(pl.n_groups) : 0; break;
         case 12: {
             want = pl.group_row.empty() ? 0 : sizeof(int) * pl.group_row.size();
             if (bytes != want) break;

@@ -86,9 +86,13 @@ struct PersistArgs {
     const int4 *ptask;        // per ticket: {lpanel offset, or -1 - segment; steps; row group | accumulate << 16 | final << 17;
                               //              completed tasks of that row group the task waits for}
     int total;                // tickets
-    unsigned int *ctr;        // [0] ticket, [1] exited warps, [2 + g] completed tasks of row group g; zero between runs
+    unsigned int *ctr;        // counters, one per 128-byte line (kCtrStride words apart): [0] ticket, [1] exited warps,
+                              // [2 + g] completed tasks of row group g — zero between runs — then the watchdog's line
     int n_groups;
+    int batch;                // tickets a warp draws at once while the launch is far from its end (1 over its last stretch)
 };
+constexpr int kCtrStride = 32;   // words between counters: each on its own L2 line (same-line atomics serialise)
+inline size_t ctr_words(int n_groups) { return (size_t)(2 + n_groups + 1) * kCtrStride; }
 
 // The plan of one column block (the whole matrix when there is a single block).
 struct BlockPlan {
@@ -128,8 +132,9 @@ struct Plan {
     bool persistent = false;
     int n_groups = 1;               // row groups: band b+1's tasks of a group wait for band b's tasks of the same group
     std::vector<int> group_row;     // [n_groups + 1] first row of each group
-    unsigned int *d_ctr = nullptr;  // [2 + n_groups] ticket, exited warps, per-group completion counters
+    unsigned int *d_ctr = nullptr;  // ticket, exited warps, per-group completion counters, watchdog (ctr_words)
     int persist_grid = 0;           // CTAs of the persistent launch (all co-resident)
+    int ticket_batch = 1;           // tickets drawn at once far from the end of the launch
     int n_ptask = 0;
     int4 *d_ptask = nullptr;        // the ticket list
     SegDesc *d_pseg_desc = nullptr; // segments of all bands with absolute panel offsets
@@ -149,7 +154,7 @@ struct spmm_b200_handle {
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
     long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = -1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0,
-              opt_zero_copy = 1, opt_persistent = -1, opt_row_groups = 0;
+              opt_zero_copy = 1, opt_persistent = -1, opt_row_groups = 0, opt_ticket_batch = 0;
     int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;

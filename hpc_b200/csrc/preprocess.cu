@@ -114,9 +114,12 @@ int auto_col_blocks(long long b_rows, int feat, long long nnz, int num_v) {
 // of all lane groups, so the kernel reads whole batches without bounds checks.
 int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder, int skip_empty, int pad,
                    std::vector<int> &row_perm, std::vector<int> &heavy_rows, std::vector<int> &heavy_seg0,
-                   std::vector<SegDesc> &segs, long long *panel_len_out) {
+                   std::vector<SegDesc> &segs, long long *panel_len_out, int row0 = 0, int row1 = -1) {
+    // natural order may be planned for a row range [row0, row1) on its own (row groups are planned in parallel)
+    if (row1 < 0) row1 = M;
+    const int base = reorder ? 0 : row0, count = reorder ? M : row1 - row0;
     // stable counting sort by bucket, descending
-    std::vector<int> order((size_t)M);
+    std::vector<int> order((size_t)count);
     if (reorder) {
         size_t cnt[34] = {0};
         for (int r = 0; r < M; ++r) {
@@ -135,16 +138,16 @@ int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder
         }
         for (int r = 0; r < M; ++r) order[start[bit_length((unsigned)(re[r] - rb[r]))]++] = r;
     } else {
-        for (int r = 0; r < M; ++r) order[r] = r;
+        for (int r = 0; r < count; ++r) order[r] = base + r;
     }
 
     row_perm.clear();
     heavy_rows.clear();
     heavy_seg0.clear();
     segs.clear();
-    row_perm.reserve(M);
+    row_perm.reserve(count);
     long long panel_len = 0;
-    for (int k = 0; k < M; ++k) {
+    for (int k = 0; k < count; ++k) {
         const int r = order[k];
         const int begin = rb[r];
         const int d = re[r] - begin;
@@ -272,12 +275,143 @@ static int block_reorder(const spmm_b200_handle *h, const int *rb, const int *re
     return (p.lanes == 32 && p.slots > 0 && total >= 8ll * p.slots * 64) ? 0 : 1;
 }
 
+static void plan_block_host(const spmm_b200_handle *h, const int *rb, const int *re, int skip_empty, int reorder, const int *group_row,
+                            int n_groups, HostBlock &hb);
+
+// Natural row order: the row groups are planned independently of each other — a task never spans a group bound, so
+// planning group by group and concatenating (offsets shifted by what precedes) IS the sequential plan with its tasks
+// cut at the bounds; the groups run in parallel on the host (OpenMP), which is what brings preprocess for the
+// products shape (2.4 M rows) from ~75 ms of serial host work to a few ms.
+static void plan_block_natural(const spmm_b200_handle *h, const int *rb, const int *re, int skip_empty, const int *group_row,
+                               int n_groups, HostBlock &hb) {
+    const Plan &p = h->plan;
+    const int M = h->num_v;
+    const int groups = 32 / p.lanes, pad = 4 * groups;
+    hb.reorder = 0;
+    struct Part {
+        std::vector<int> row_perm, heavy_rows, heavy_seg0, cost, dst;
+        std::vector<SegDesc> segs;
+        std::vector<int2> ltasks, utask;
+        long long panel_len = 0, lpanel_len = 0, total_cost = 0;
+        int rc = 0;
+    };
+    std::vector<Part> part((size_t)n_groups);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int g = 0; g < n_groups; ++g) {
+        Part &x = part[g];
+        x.rc = plan_rows_host(rb, re, M, p.seg_len, 0, skip_empty, pad, x.row_perm, x.heavy_rows, x.heavy_seg0, x.segs, &x.panel_len,
+                              group_row[g], group_row[g + 1]);
+        x.cost.resize(x.row_perm.size());
+        for (size_t i = 0; i < x.row_perm.size(); ++i) {
+            x.cost[i] = re[x.row_perm[i]] - rb[x.row_perm[i]] + 1;
+            x.total_cost += x.cost[i];
+        }
+    }
+    long long total = 0, n_seg = 0;
+    for (Part &x : part) {
+        if (x.rc) {
+            hb.rc = x.rc;
+            snprintf(hb.err, sizeof(hb.err), "row planning failed");
+            return;
+        }
+        total += x.total_cost;
+        n_seg += (long long)x.segs.size();
+    }
+    int steps = p.light_steps;
+    if (h->opt_light_steps <= 0) steps = auto_light_steps(groups, total, p.slots, n_seg * p.n_slices);
+    hb.light_steps = steps;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int g = 0; g < n_groups; ++g) {
+        Part &x = part[g];
+        const int n = (int)x.row_perm.size();
+        x.dst.resize((size_t)n);
+        x.lpanel_len = pack_light_host(x.cost.data(), n, groups, steps, x.dst.data(), x.ltasks);
+        // light tasks and heavy segments merged by the row they start with
+        x.utask.reserve(x.ltasks.size() + x.segs.size());
+        size_t li = 0, si = 0, first_i = 0;
+        while (li < x.ltasks.size() || si < x.segs.size()) {
+            int lrow = 0x7fffffff;
+            if (li < x.ltasks.size()) {
+                while (first_i < (size_t)n && x.dst[first_i] < x.ltasks[li].x) ++first_i;
+                if (first_i < (size_t)n) lrow = x.row_perm[first_i];
+            }
+            if (si < x.segs.size() && x.segs[si].row < lrow) {
+                x.utask.push_back(make_int2(-1 - (int)si, 0));
+                ++si;
+            } else {
+                x.utask.push_back(x.ltasks[li]);
+                ++li;
+            }
+        }
+    }
+    // concatenate, shifting every offset by what precedes
+    std::vector<long long> b_light((size_t)n_groups + 1, 0), b_heavy((size_t)n_groups + 1, 0), b_seg((size_t)n_groups + 1, 0),
+        b_panel((size_t)n_groups + 1, 0), b_lpanel((size_t)n_groups + 1, 0), b_ltask((size_t)n_groups + 1, 0), b_utask((size_t)n_groups + 1, 0);
+    for (int g = 0; g < n_groups; ++g) {
+        const Part &x = part[g];
+        b_light[g + 1] = b_light[g] + (long long)x.row_perm.size();
+        b_heavy[g + 1] = b_heavy[g] + (long long)x.heavy_rows.size();
+        b_seg[g + 1] = b_seg[g] + (long long)x.segs.size();
+        b_panel[g + 1] = b_panel[g] + x.panel_len;
+        b_lpanel[g + 1] = b_lpanel[g] + x.lpanel_len;
+        b_ltask[g + 1] = b_ltask[g] + (long long)x.ltasks.size();
+        b_utask[g + 1] = b_utask[g] + (long long)x.utask.size();
+    }
+    hb.panel_len = b_panel[n_groups];
+    hb.lpanel_len = b_lpanel[n_groups];
+    if (hb.panel_len > 0x7fffffffll || hb.lpanel_len > 0x7fffffffll) {
+        hb.rc = SPMM_B200_EINVAL;
+        snprintf(hb.err, sizeof(hb.err), "panel too large");
+        return;
+    }
+    hb.row_perm.resize((size_t)b_light[n_groups]);
+    hb.light.resize((size_t)b_light[n_groups]);
+    hb.heavy_rows.resize((size_t)b_heavy[n_groups]);
+    hb.heavy_seg0.resize(b_heavy[n_groups] ? (size_t)b_heavy[n_groups] + 1 : 0);
+    hb.segs.resize((size_t)b_seg[n_groups]);
+    hb.seg_hrow.resize((size_t)b_seg[n_groups]);
+    hb.ltasks.resize((size_t)b_ltask[n_groups]);
+    hb.utask.resize((size_t)b_utask[n_groups]);
+    hb.task_group.resize((size_t)b_utask[n_groups]);
+    if (b_heavy[n_groups]) hb.heavy_seg0[(size_t)b_heavy[n_groups]] = (int)b_seg[n_groups];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int g = 0; g < n_groups; ++g) {
+        const Part &x = part[g];
+        const int lp = (int)b_lpanel[g], pn = (int)b_panel[g], sg = (int)b_seg[g], hv = (int)b_heavy[g];
+        for (size_t i = 0; i < x.row_perm.size(); ++i) {
+            const int r = x.row_perm[i];
+            hb.row_perm[(size_t)b_light[g] + i] = r;
+            hb.light[(size_t)b_light[g] + i] = make_int4(r, rb[r], re[r] - rb[r], lp + x.dst[i]);
+        }
+        for (size_t i = 0; i < x.heavy_rows.size(); ++i) {
+            hb.heavy_rows[(size_t)hv + i] = x.heavy_rows[i];
+            hb.heavy_seg0[(size_t)hv + i] = sg + x.heavy_seg0[i];
+            for (int sgm = x.heavy_seg0[i]; sgm < x.heavy_seg0[i + 1]; ++sgm) hb.seg_hrow[(size_t)sg + sgm] = hv + (int)i;
+        }
+        for (size_t i = 0; i < x.segs.size(); ++i) {
+            SegDesc d = x.segs[i];
+            d.panel_off += pn;
+            hb.segs[(size_t)sg + i] = d;
+        }
+        for (size_t i = 0; i < x.ltasks.size(); ++i) hb.ltasks[(size_t)b_ltask[g] + i] = make_int2(lp + x.ltasks[i].x, x.ltasks[i].y);
+        for (size_t i = 0; i < x.utask.size(); ++i) {
+            const int2 u = x.utask[i];
+            hb.utask[(size_t)b_utask[g] + i] = u.x < 0 ? make_int2(-1 - (sg + (-1 - u.x)), 0) : make_int2(lp + u.x, u.y);
+            hb.task_group[(size_t)b_utask[g] + i] = g;
+        }
+    }
+}
+
 // Host part of one block: row order, segments, light-stream packing, task order, row group of every task.
 // group_row: NULL, or the n_groups + 1 row-group boundaries (natural order only).
 static void plan_block_host(const spmm_b200_handle *h, const int *rb, const int *re, int skip_empty, int reorder,
                             const int *group_row, int n_groups, HostBlock &hb) {
     const Plan &p = h->plan;
     const int M = h->num_v;
+    if (reorder == 0 && !p.scalar && group_row) {
+        plan_block_natural(h, rb, re, skip_empty, group_row, n_groups, hb);
+        return;
+    }
     hb.reorder = reorder;
     const int pad = p.scalar ? 2 : 4 * (32 / p.lanes);
     hb.rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, pad, hb.row_perm, hb.heavy_rows, hb.heavy_seg0, hb.segs,
@@ -461,21 +595,46 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     auto row_begin = [&](int b) { return nb > 1 ? split.data() + (size_t)b * M : ptr.data(); };
     auto row_end = [&](int b) { return nb > 1 ? split.data() + (size_t)(b + 1) * M : ptr.data() + 1; };
 
-    // One persistent launch for all column blocks (option "persistent": -1 auto = whenever there are several, 1 = also
-    // for a single block, 0 = one launch per block). Needs a single feature slice (K <= 256).
-    p.persistent = !p.scalar && p.n_slices == 1 && nb <= kMaxBands &&
-                   (h->opt_persistent == 1 || (h->opt_persistent < 0 && nb > 1));
+    // One persistent launch for all column blocks (option "persistent": 1 = always, 0 = one launch per block, -1 =
+    // automatic). Needs a single feature slice (K <= 256). Measured on B200 (profiles/r02_persistent.md), one rank's block
+    // of an N-way partition of the reddit shape, K = 256, against one launch per block: -1.4 % / -2.8 % / -4.2 % / -4.2 %
+    // at N = 2 / 3 / 4 / 6 (shortest block 28 / 19 / 14 / 9 waves of resident warps: the tail of every pass overlaps the
+    // next), +2 % at N = 1 (45 waves: nothing to gain, and the ticket bookkeeping costs a little) and +10 % at N = 8
+    // (7 waves: a task's completion is published during the warp's next task, and with passes this short the next
+    // pass's tasks of the same row group arrive before that and wait). Automatic = inside the window that pays.
+    bool persistent = !p.scalar && p.n_slices == 1 && nb <= kMaxBands && h->opt_persistent == 1;
+    if (!p.scalar && p.n_slices == 1 && nb > 1 && nb <= kMaxBands && h->opt_persistent < 0 && p.slots > 0) {
+        double shortest = 1e30;
+        for (int b = 0; b < nb; ++b) {
+            long long total = M;
+            const int *rb = row_begin(b), *re = row_end(b);
+            for (int r = 0; r < M; ++r) total += re[r] - rb[r];
+            const double tasks = (double)total / (total >= 64ll * p.slots * 64 ? 128 : 64);   // the automatic task sizes
+            shortest = std::min(shortest, tasks / (double)p.slots);
+        }
+        persistent = shortest >= 8.0 && shortest <= 36.0;
+    }
+    p.persistent = persistent;
     // Row order per block, then row groups: in natural order the rows are cut into n_groups contiguous groups balanced by
     // nonzeros; a task never spans a group, and a task of band b+1 waits for the tasks of band b that own its group.
     // Bucketed order has no contiguous groups: one group (a band then waits for the whole band before it).
     std::vector<int> reorder(nb);
     bool all_natural = true;
-    for (int b = 0; b < nb; ++b) {
-        reorder[b] = block_reorder(h, row_begin(b), row_end(b));
-        all_natural &= reorder[b] == 0;
+    if (p.persistent && h->opt_reorder < 0) {
+        // one launch over all blocks: its length is what decides between the two orders, not each block's own (the
+        // blocks of a rank's row partition are uneven — the block around the diagonal holds the graph's local half)
+        const long long total = (long long)h->num_e + (long long)M * nb;
+        const int r = (p.lanes == 32 && p.slots > 0 && total >= 8ll * p.slots * 64) ? 0 : 1;
+        for (int b = 0; b < nb; ++b) reorder[b] = r;
+        all_natural = r == 0;
+    } else {
+        for (int b = 0; b < nb; ++b) {
+            reorder[b] = block_reorder(h, row_begin(b), row_end(b));
+            all_natural &= reorder[b] == 0;
+        }
     }
     p.n_groups = 1;
-    if (p.persistent && nb > 1 && all_natural) {
+    if (!p.scalar && all_natural) {
         long long g = h->opt_row_groups > 0 ? h->opt_row_groups : 16;
         if (g > kMaxRowGroups) g = kMaxRowGroups;
         if (g > M) g = M;
@@ -491,13 +650,12 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
 
     // ---- host planning of every block (independent of each other) -------------------------------------------------
     std::vector<HostBlock> hb((size_t)nb);
-#pragma omp parallel for schedule(dynamic, 1) if (nb > 1)
+    // (the row groups inside a block are planned in parallel; the blocks one after the other)
     for (int b = 0; b < nb; ++b) {
         // passes after the first skip rows without nonzeros in their band — except the last pass, which lists every
         // row: it is the one that delivers final rows (to C, to the stacked-layer targets, to run_host's host buffer)
         const bool skip_empty = b > 0 && b + 1 != nb;
-        plan_block_host(h, row_begin(b), row_end(b), skip_empty, reorder[b], p.n_groups > 1 ? p.group_row.data() : nullptr,
-                        p.n_groups, hb[b]);
+        plan_block_host(h, row_begin(b), row_end(b), skip_empty, reorder[b], all_natural ? p.group_row.data() : nullptr, p.n_groups, hb[b]);
     }
     for (int b = 0; b < nb; ++b)
         if (hb[b].rc) {
@@ -619,10 +777,16 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         if ((rc = upload_vec(&p.d_pseg_desc, pseg, stream))) return rc;
         if ((rc = upload_vec(&p.d_pseg_hrow, pseg_hrow, stream))) return rc;
         if ((rc = upload_vec(&p.d_pheavy_seg0, pheavy_seg0, stream))) return rc;
-        // ticket, exited warps, per-group completions, 8 watchdog words
-        SB_CUDA(cudaMalloc((void **)&p.d_ctr, sizeof(unsigned int) * (size_t)(2 + p.n_groups + 8)));
-        SB_CUDA(cudaMemsetAsync(p.d_ctr, 0, sizeof(unsigned int) * (size_t)(2 + p.n_groups + 8), stream));
+        // ticket, exited warps, per-group completions, watchdog: one 128-byte line each
+        SB_CUDA(cudaMalloc((void **)&p.d_ctr, sizeof(unsigned int) * ctr_words(p.n_groups)));
+        SB_CUDA(cudaMemsetAsync(p.d_ctr, 0, sizeof(unsigned int) * ctr_words(p.n_groups), stream));
         p.persist_grid = persistent_grid(p.lanes, p.vec, p.tune, p.block);
+        // Tickets per draw. A batch delays the completion of its last task by the tasks before it, and the next band's
+        // tasks of the same row group wait for that: only bands much longer than the batches of all resident warps
+        // (32 waves) draw four at a time; the ticket counter's L2 line takes one atomic per draw either way.
+        long long shortest = task_total;
+        for (int b = 0; b < nb; ++b) shortest = std::min<long long>(shortest, (long long)hb[b].utask.size());
+        p.ticket_batch = h->opt_ticket_batch > 0 ? (int)h->opt_ticket_batch : (p.slots > 0 && shortest >= 32 * p.slots ? 4 : 1);
         if (p.persist_grid <= 0) p.persistent = false;   // occupancy could not be queried: one launch per block
     }
     SB_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope

@@ -30,6 +30,7 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kChunk = 128;   // panel entries per TMA stage (1 KB)
 constexpr int kStages = 2;
+constexpr int kWarpSlots = 8;   // words of per-warp bookkeeping in shared memory (persistent kernel)
 
 // ---- memory helpers ------------------------------------------------------------------------
 
@@ -86,7 +87,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
-// Watchdog of the persistent launch (wd = a.ctr + 2 + n_groups, 8 words, NULL elsewhere): a wait that lasts longer than
+// Watchdog of the persistent launch (wd = the last line of a.ctr, NULL elsewhere): a wait that lasts longer than
 // ~2 s of SM clocks records what it was waiting for — {kind, a, b, c, d} — once, and gives up, so a scheduling bug
 // shows up as a wrong result with a diagnosis instead of a hung GPU. kind 1: staged chunk (TMA), 2: row-group dependency.
 constexpr long long kWatchdogClocks = 4000000000ll;
@@ -197,6 +198,7 @@ __device__ __forceinline__ const int2 *pipe_wait(const Pipe &p, int k) {
 
 struct NoHook {
     __device__ __forceinline__ void start() const {}
+    __device__ __forceinline__ void mid() const {}
     __device__ __forceinline__ void late() const {}
 };
 
@@ -301,6 +303,7 @@ __device__ __forceinline__ void light_stream(const CommonArgs &c, const BandArgs
         __syncwarp();   // every lane is done reading this stage before it is refilled
         if (lane == 0 && k + kStages < nchunks)
             pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, len - (k + kStages) * kChunk));
+        if (k == 0) hook.mid();
     }
     pipe_finish(pipe, nchunks, lane);
     hook.late();
@@ -367,6 +370,7 @@ __device__ __forceinline__ void heavy_segment(const CommonArgs &c, const BandArg
         __syncwarp();   // every lane is done reading this stage before it is refilled
         if (lane == 0 && k + kStages < nchunks)
             pipe_issue(pipe, k + kStages, src + (size_t)(k + kStages) * kChunk, (uint32_t)min(kChunk, plen - (k + kStages) * kChunk));
+        if (k == 0) hook.mid();
     }
     pipe_finish(pipe, nchunks, lane);
     hook.late();
@@ -443,62 +447,100 @@ __global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_kernel(
 __device__ __forceinline__ void red_release_gpu(unsigned int *p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+// The poll of a row group's counter. Not ld.acquire: that compiles to LDG.STRONG.GPU + CCTL.IVALL — an invalidation of
+// the SM's whole L1 per poll. The rows read after a successful poll are read with ld.cg (L2, never L1), so a relaxed
+// poll followed by fence.acq_rel.gpu (MEMBAR.ALL.GPU, no invalidation) gives the ordering that is needed.
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+#ifdef SPMM_B200_PERSIST_STATS
+#define PSTAT(i, v) atomicAdd(reinterpret_cast<unsigned long long *>(wd + 8) + (i), (unsigned long long)(v))
+#else
+#define PSTAT(i, v) ((void)0)
+#endif
 
 // The persistent warp's bookkeeping around a task.
-//   start()  once the task's first chunks are on their way: request the next ticket (parked in shared memory while the
+//   start()  once the task's first chunks are on their way: settle the next ticket (parked in shared memory while the
 //            task runs) and check the dependency — the tasks of earlier bands that own the same row group must have
-//            completed. The two round trips to L2 overlap each other and the TMA copy already under way.
-//   late()   right before the task's final stores: publish the completion of the PREVIOUS task (one release-add to its
-//            row group's counter). That late, the previous task's stores were acknowledged long ago, so the release
-//            does not stall; issued at the start of the task it would wait for the row the warp has just flushed.
+//            completed. Tickets are drawn four at a time while the launch is far from its end and one at a time over
+//            its last stretch (the tail stays fine-grained); the dependency is polled only when the cached count of
+//            that row group does not already cover it (consecutive tasks of a warp mostly share band and group). Both
+//            keep the traffic on the counters' L2 lines — where same-line atomics serialise — far below their limit.
+//   mid()    after the task's first chunk: publish the completion of the PREVIOUS task (one release-add to its row
+//            group's counter). By then the previous task's stores were acknowledged, so the release does not stall;
+//            issued at the start of the task it would wait for the row the warp has just flushed, and issued at the
+//            end of the task it would delay the tasks that wait for it by a whole (possibly long) task.
+//   late()   right before the task's final stores: note this task as finished-but-unpublished.
 // A warp that has to block in start() publishes first: the tasks it waits for can include its own previous one.
 // Lane 0 does the counting; the warp barriers at the end of every chunk and of every task order all lanes' stores
 // before lane 0's release and extend its acquire to them (the pattern of a grid barrier).
 struct PersistHook {
     unsigned int *ticket;
-    unsigned int *grp_done;
-    volatile unsigned int *slot;   // [0] next ticket, [1] row group of the finished, unpublished task + 1 (0: none)
+    unsigned int *grp_done;        // counter of row group g at grp_done[g * kCtrStride]
+    volatile unsigned int *slot;   // per warp: [0] next ticket, [1] end of the drawn batch, [2] row group of the finished,
+                                   // unpublished task + 1 (0: none), [3] row group whose count is cached + 1, [4] that count
+    unsigned int t;                // this task's ticket
+    int total;
+    int batch;
     int flags;                     // this task: row group | accumulate << 16 | final << 17
     int need;                      // completed tasks of that group this task waits for (0: none)
     int lane;
     unsigned int *wd;
     __device__ __forceinline__ void start() const {
         if (lane == 0) {
-            const unsigned int next = atomicAdd(ticket, 1u);
-            if (need > 0) {
-                const unsigned int *cnt = grp_done + (flags & 0xffff);
-                unsigned int seen = ld_acquire_gpu(cnt);
+            unsigned int next = t + 1, fresh = 0;
+            const bool draw = next >= slot[1];
+            if (draw) {
+                // far from the end (more than 16 tasks per warp left): four tickets at once
+                fresh = (unsigned int)total > t && (unsigned int)total - t > 16u * gridDim.x * (blockDim.x >> 5) ? (unsigned int)batch : 1u;
+                next = atomicAdd(ticket, fresh);
+            }
+            const unsigned int grp = (unsigned int)(flags & 0xffff);
+            if (need > 0 && !(slot[3] == grp + 1 && (int)slot[4] >= need)) {
+                const unsigned int *cnt = grp_done + grp * kCtrStride;
+                unsigned int seen = ld_relaxed_gpu(cnt);
+                PSTAT(0, 1);
                 if ((int)seen < need) {
-                    const unsigned int p = slot[1];
+                    const unsigned int p = slot[2];
                     if (p) {
-                        red_release_gpu(grp_done + (p - 1));
-                        slot[1] = 0;
+                        red_release_gpu(grp_done + (p - 1) * kCtrStride);
+                        slot[2] = 0;
                     }
                     const long long t0 = clock64();
-                    while ((int)(seen = ld_acquire_gpu(cnt)) < need) {
+                    while ((int)(seen = ld_relaxed_gpu(cnt)) < need) {
                         __nanosleep(32);
                         if (clock64() - t0 > kWatchdogClocks) {
-                            watchdog_trip(wd, 2u, (unsigned int)(flags & 0xffff), (unsigned int)need, seen, blockIdx.x * blockDim.x + threadIdx.x);
+                            watchdog_trip(wd, 2u, grp, (unsigned int)need, seen, blockIdx.x * blockDim.x + threadIdx.x);
                             break;
                         }
                     }
+                    PSTAT(1, 1);
+                    PSTAT(2, clock64() - t0);
                 }
+                fence_acq_rel_gpu();
+                slot[3] = grp + 1;
+                slot[4] = seen;
             }
             slot[0] = next;
+            if (draw) slot[1] = next + fresh;
         }
         __syncwarp();   // extends lane 0's acquire to the lanes that read C rows of the earlier band
     }
-    __device__ __forceinline__ void late() const {
+    __device__ __forceinline__ void mid() const {
         if (lane == 0) {
-            const unsigned int p = slot[1];
-            if (p) red_release_gpu(grp_done + (p - 1));
-            slot[1] = ((flags >> 17) & 1) ? 0u : (unsigned int)(flags & 0xffff) + 1u;   // nobody waits for the last band
+            const unsigned int p = slot[2];
+            if (p) {
+                red_release_gpu(grp_done + (p - 1) * kCtrStride);
+                slot[2] = 0;
+            }
         }
+    }
+    __device__ __forceinline__ void late() const {
+        // this task counts as finished once its final stores are issued (published during the next task)
+        if (lane == 0) slot[2] = ((flags >> 17) & 1) ? 0u : (unsigned int)(flags & 0xffff) + 1u;   // nobody waits for the last band
     }
 };
 
@@ -508,37 +550,39 @@ __global__ void __launch_bounds__(256, Tune<TUNE, VEC>::kMinBlocks) spmm_persist
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
-    unsigned int *const ticket = a.ctr, *const exited = a.ctr + 1, *const grp_done = a.ctr + 2;
+    unsigned int *const ticket = a.ctr, *const exited = a.ctr + kCtrStride, *const grp_done = a.ctr + 2 * kCtrStride;
     const Pipe pipe = {reinterpret_cast<int2 *>(smem_raw) + (size_t)warp * kStages * kChunk,
                        reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * kStages * kChunk * sizeof(int2)) + warp * kStages,
-                       a.ctr + 2 + a.n_groups};
-    // two words of shared memory per warp (after the barriers): its next ticket, and its unpublished completion
+                       a.ctr + (2 + a.n_groups) * kCtrStride};
+    // a few words of shared memory per warp (after the barriers): see PersistHook::slot
     volatile unsigned int *slot =
-        reinterpret_cast<unsigned int *>(smem_raw + (size_t)nwarps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t))) + 2 * warp;
+        reinterpret_cast<unsigned int *>(smem_raw + (size_t)nwarps * kStages * (kChunk * sizeof(int2) + sizeof(uint64_t))) + kWarpSlots * warp;
     pipe_init(pipe, lane);
     unsigned int t = 0;
     if (lane == 0) {
         t = atomicAdd(ticket, 1u);
-        slot[1] = 0;
+        slot[1] = t + 1;
+        slot[2] = 0;
+        slot[3] = 0;
     }
     t = __shfl_sync(kFull, t, 0);
     while (t < (unsigned int)a.total) {
         // {lpanel offset | -1 - segment, steps, row group | accumulate << 16 | final << 17, completions to wait for}
         const int4 pt = __ldg(a.ptask + t);
         const bool accumulate = (pt.z >> 16) & 1, final = (pt.z >> 17) & 1;
-        const PersistHook hook = {ticket, grp_done, slot, pt.z, pt.w, lane, pipe.wd};
+        const PersistHook hook = {ticket, grp_done, slot, t, a.total, a.batch, pt.z, pt.w, lane, pipe.wd};
         if (pt.x < 0) heavy_segment<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, -1 - pt.x, lane, pipe, hook);
         else light_stream<LANES, VEC, TUNE, FULL>(a.c, a.all, accumulate, final, 0, make_int2(pt.x, pt.y), lane, pipe, hook);
         __syncwarp();   // every lane's stores of this task precede whatever lane 0 releases next
         t = slot[0];
     }
     // the last task's completion
-    if (lane == 0 && slot[1]) red_release_gpu(grp_done + (slot[1] - 1));
+    if (lane == 0 && slot[2]) red_release_gpu(grp_done + (slot[2] - 1) * kCtrStride);
     // the last warp out returns the counters to zero for the next run (nobody is left to read them)
     if (lane == 0) {
         const unsigned int total_warps = gridDim.x * nwarps;
         if (atomicAdd(exited, 1u) == total_warps - 1) {
-            for (int g = 0; g < a.n_groups; ++g) grp_done[g] = 0;
+            for (int g = 0; g < a.n_groups; ++g) grp_done[g * kCtrStride] = 0;
             *ticket = 0;
             *exited = 0;
             __threadfence();
@@ -682,8 +726,8 @@ __global__ void __launch_bounds__(256) valid_kernel(const float *y, const float 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
 }
 
-// per warp: kStages chunks + their mbarriers, and two words for the persistent kernel (parked ticket, unpublished completion)
-size_t task_smem(int block) { return (size_t)(block / 32) * (kStages * (kChunk * sizeof(int2) + sizeof(uint64_t)) + 2 * sizeof(unsigned int)); }
+// per warp: kStages chunks + their mbarriers, and kWarpSlots words of bookkeeping for the persistent kernel
+size_t task_smem(int block) { return (size_t)(block / 32) * (kStages * (kChunk * sizeof(int2) + sizeof(uint64_t)) + kWarpSlots * sizeof(unsigned int)); }
 
 template <int LANES, int VEC, int TUNE, bool FULL>
 void launch_tuned(const RunArgs &a, int block, cudaStream_t stream) {
@@ -823,6 +867,7 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         a.total = p.n_ptask;
         a.ctr = p.d_ctr;
         a.n_groups = p.n_groups;
+        a.batch = p.ticket_batch;
         if (a.total > 0) {
             int rc = launch_lanes(p, a, full, stream, p.persist_grid);
             if (rc) return rc;

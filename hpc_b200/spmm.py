@@ -182,7 +182,7 @@ class SpMMB200(SpMM):
                                (8, "ltask", info["n_ltask"] * 2), (9, "lpanel", info["lpanel_len"] * 2),
                                (10, "utask", info["n_utask"] * 2), (11, "ptask", info["n_tickets"] * 4),
                                (12, "group_row", info["n_row_groups"] + 1),
-                               (13, "counters", 2 + info["n_row_groups"] + 8 if info["persistent"] else 0)):
+                               (13, "counters", (2 + info["n_row_groups"] + 1) * 32 if info["persistent"] else 0)):
             a = np.empty(n, dtype=np.int32)
             check(lib.spmm_b200_plan_copy(self._h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
             out[name] = a

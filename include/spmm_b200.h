@@ -179,9 +179,10 @@ int spmm_b200_plan_info(spmm_b200_t h, spmm_b200_plan_info_t *info);
  *  11 ptask      int32[n_tickets*4]  the persistent launch's ticket list, band-major (not per block): {lpanel offset
  *                                   over all blocks, or -1 - segment over all blocks; steps; row group | accumulate << 16
  *                                   | final << 17; completed tasks of that row group the task waits for}
- *  13 counters   uint32[2+n_row_groups+8] the persistent launch's counters {ticket, exited warps, completions per row
- *                                   group} — all zero between runs — and its 8 watchdog words {kind, ...}: non-zero
- *                                   kind = a wait inside the launch timed out (1 staged chunk, 2 row-group dependency)
+ *  13 counters   uint32[(2+n_row_groups+1)*32] the persistent launch's counters, one per 128-byte line (word 32*i):
+ *                                   ticket, exited warps, completions per row group — all zero between runs — then the
+ *                                   watchdog's line {kind, ...}: non-zero kind = a wait inside the launch timed out
+ *                                   (1 staged chunk, 2 row-group dependency)
  *  12 group_row  int32[n_row_groups+1] first row of each row group (row g's bound: first row with ptr >= g*nnz/groups)
  * Returns SPMM_B200_EINVAL when `bytes` is not the exact size. */
 int spmm_b200_plan_copy(spmm_b200_t h, int which, void *host_dst, size_t bytes);

@@ -369,7 +369,10 @@ def test_plan_matches_oracle(shape, seg_len, reorder):
     got = op.plan_arrays()
     assert info["seg_len"] == (seg_len or P.auto_seg_len(len(idx), 32))
     assert info["kslice"] == P.auto_kslice(g.num_v, 32)
-    want.update(P.light_stream(want, idx, g.val.cpu().numpy(), 32 // info["lanes"], info["light_steps"], k4=8))
+    # natural order: the rows are planned in 16 row groups (tasks cut at the bounds); bucketed order: one group
+    assert info["n_row_groups"] == (1 if reorder else 16)
+    group_row = None if reorder else P.partition_rows(ptr, info["n_row_groups"])
+    want.update(P.light_stream(want, idx, g.val.cpu().numpy(), 32 // info["lanes"], info["light_steps"], k4=8, group_row=group_row))
     want["utask"] = P.unified_tasks(want, want, bool(reorder))
     assert np.array_equal(got["utask"], want["utask"]) and info["n_utask"] == info["n_ltask"] + info["n_seg"]
     total = int(want["light_desc"][:, 2].astype(np.int64).sum()) + len(want["light_desc"])
@@ -433,7 +436,7 @@ def test_persistent_plan_matches_oracle(shape, K, nb, seg_len, groups):
     op.preprocess(vin, vout)
     info = op.plan_info(0)
     assert info["persistent"] == 1 and info["n_col_blocks"] == nb
-    want_groups = (groups or 16) if (natural and nb > 1) else 1
+    want_groups = (groups or 16) if natural else 1
     assert info["n_row_groups"] == want_groups
     M = g.num_v
     val = g.val.cpu().numpy()

@@ -34,7 +34,7 @@ for rep in range(6):
     t = time.perf_counter()
     op.run(vin, got); torch.cuda.synchronize()
     print("run", rep, round((time.perf_counter() - t) * 1e3, 3), "ms equal:", bool(torch.equal(got, want)), "launches", op.launches_per_run,
-          "counters", op.plan_arrays()["counters"].view(np.uint32).tolist(), flush=True)
+          "counters nonzero:", int(np.count_nonzero(op.plan_arrays()["counters"])), flush=True)
 '''
 import json
 for shape, K, opts in CASES:
