@@ -274,6 +274,15 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
+            # one process per GPU: run on the cores next to this GPU, so that the pinned host buffers of the host-buffer
+            # call are allocated NUMA-local to its PCIe link (what `numactl` would do around each rank)
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.local))
+            except Exception:
+                pass
+        if self.world > 1:
             # keep stdout to the one JSON line: whatever NCCL prints while it initialises ("NCCL version ..." is a
             # bare printf at NCCL_DEBUG=VERSION) is sent to stderr by pointing fd 1 at fd 2 for the duration
             sys.stdout.flush()
