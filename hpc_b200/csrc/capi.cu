@@ -84,6 +84,7 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     else if (!strcmp(name, "persistent") && value >= -1 && value <= 1) h->opt_persistent = value;
     else if (!strcmp(name, "row_groups") && value >= 0 && value <= kMaxRowGroups) h->opt_row_groups = value;
     else if (!strcmp(name, "ticket_batch") && value >= 0 && value <= 16) h->opt_ticket_batch = value;
+    else if (!strcmp(name, "split_streams") && value >= -1 && value <= 1) h->opt_split_streams = value;
     else if (!strcmp(name, "zero_copy") && value >= 0 && value <= 1) {
         h->opt_zero_copy = value;   // run_host only; not part of the plan
         return 0;
@@ -290,6 +291,9 @@ int spmm_b200_destroy(spmm_b200_t h) {
     cudaFree(h->d_stage_out);
     for (cudaEvent_t e : h->band_events) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->aux_fork) cudaEventDestroy(h->aux_fork);
+    if (h->aux_join) cudaEventDestroy(h->aux_join);
     delete h;
     return 0;
 }

@@ -117,6 +117,7 @@ struct BlockPlan {
     int2 *d_panel = nullptr;
     float *d_part = nullptr;
     std::vector<int> task_group;   // host: row group of every utask entry (persistent launch)
+    int split_task = 0;            // first task of the second half of the row groups (two-stream launches); 0 / n_utask: no split
 };
 
 struct Plan {
@@ -135,6 +136,7 @@ struct Plan {
     unsigned int *d_ctr = nullptr;  // ticket, exited warps, per-group completion counters, watchdog (ctr_words)
     int persist_grid = 0;           // CTAs of the persistent launch (all co-resident)
     int ticket_batch = 1;           // tickets drawn at once far from the end of the launch
+    bool split_streams = false;     // every pass as two launches (row-group halves) on two streams: each tail overlaps the next launch
     int n_ptask = 0;
     int4 *d_ptask = nullptr;        // the ticket list
     SegDesc *d_pseg_desc = nullptr; // segments of all bands with absolute panel offsets
@@ -154,12 +156,14 @@ struct spmm_b200_handle {
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
     long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = -1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0,
-              opt_zero_copy = 1, opt_persistent = -1, opt_row_groups = 0, opt_ticket_batch = 0;
+              opt_zero_copy = 1, opt_persistent = -1, opt_row_groups = 0, opt_ticket_batch = 0, opt_split_streams = -1;
     int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_elems = 0, stage_in_elems = 0;
     cudaStream_t copy_stream = nullptr;          // run_host: H2D of B bands
+    cudaStream_t aux_stream = nullptr;           // two-stream launches: the second row half
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     std::vector<cudaEvent_t> band_events;
     int n_gather = 0;
     float *gather[spmm_b200::kMaxGather] = {nullptr};
@@ -194,7 +198,7 @@ int refresh_panels(spmm_b200_handle *h, cudaStream_t stream);
 // (run_host uploads B band by band on a second stream while earlier passes compute)
 // cfinal: NULL, or where the final rows go instead of vout (the last pass stores them there; earlier passes keep
 // their partial chains in vout)
-int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
+int launch_spmm(spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
                 int *launches, const cudaEvent_t *band_ready = nullptr, float *cfinal = nullptr);
 int resident_warps(int lanes, int vec, int tune, int block);
 int persistent_grid(int lanes, int vec, int tune, int block);   // CTAs that are co-resident for the persistent kernel

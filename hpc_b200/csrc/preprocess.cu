@@ -115,14 +115,14 @@ int auto_col_blocks(long long b_rows, int feat, long long nnz, int num_v) {
 int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder, int skip_empty, int pad,
                    std::vector<int> &row_perm, std::vector<int> &heavy_rows, std::vector<int> &heavy_seg0,
                    std::vector<SegDesc> &segs, long long *panel_len_out, int row0 = 0, int row1 = -1) {
-    // natural order may be planned for a row range [row0, row1) on its own (row groups are planned in parallel)
+    // a row range [row0, row1) may be planned on its own (row groups are planned in parallel and concatenated)
     if (row1 < 0) row1 = M;
-    const int base = reorder ? 0 : row0, count = reorder ? M : row1 - row0;
+    const int base = row0, count = row1 - row0;
     // stable counting sort by bucket, descending
     std::vector<int> order((size_t)count);
     if (reorder) {
         size_t cnt[34] = {0};
-        for (int r = 0; r < M; ++r) {
+        for (int r = row0; r < row1; ++r) {
             const int d = re[r] - rb[r];
             if (d < 0) {
                 set_error("CSR ptr decreases at row %d", r);
@@ -136,7 +136,7 @@ int plan_rows_host(const int *rb, const int *re, int M, int seg_len, int reorder
             start[b] = run;
             run += cnt[b];
         }
-        for (int r = 0; r < M; ++r) order[start[bit_length((unsigned)(re[r] - rb[r]))]++] = r;
+        for (int r = row0; r < row1; ++r) order[start[bit_length((unsigned)(re[r] - rb[r]))]++] = r;
     } else {
         for (int r = 0; r < count; ++r) order[r] = base + r;
     }
@@ -278,16 +278,17 @@ static int block_reorder(const spmm_b200_handle *h, const int *rb, const int *re
 static void plan_block_host(const spmm_b200_handle *h, const int *rb, const int *re, int skip_empty, int reorder, const int *group_row,
                             int n_groups, HostBlock &hb);
 
-// Natural row order: the row groups are planned independently of each other — a task never spans a group bound, so
-// planning group by group and concatenating (offsets shifted by what precedes) IS the sequential plan with its tasks
-// cut at the bounds; the groups run in parallel on the host (OpenMP), which is what brings preprocess for the
-// products shape (2.4 M rows) from ~75 ms of serial host work to a few ms.
-static void plan_block_natural(const spmm_b200_handle *h, const int *rb, const int *re, int skip_empty, const int *group_row,
-                               int n_groups, HostBlock &hb) {
+// The row groups (contiguous row ranges) are planned independently of each other — a task never spans a group bound, and
+// the row order (natural or degree buckets) applies INSIDE a group — so planning group by group and concatenating
+// (offsets shifted by what precedes) is the whole plan. The groups run in parallel on the host (OpenMP), which is what
+// brings preprocess for the products shape (2.4 M rows) from ~75 ms of serial host work to a few ms. One group is the
+// ungrouped plan.
+static void plan_block_groups(const spmm_b200_handle *h, const int *rb, const int *re, int skip_empty, int reorder, const int *group_row,
+                              int n_groups, HostBlock &hb) {
     const Plan &p = h->plan;
     const int M = h->num_v;
     const int groups = 32 / p.lanes, pad = 4 * groups;
-    hb.reorder = 0;
+    hb.reorder = reorder;
     struct Part {
         std::vector<int> row_perm, heavy_rows, heavy_seg0, cost, dst;
         std::vector<SegDesc> segs;
@@ -299,7 +300,7 @@ static void plan_block_natural(const spmm_b200_handle *h, const int *rb, const i
 #pragma omp parallel for schedule(dynamic, 1)
     for (int g = 0; g < n_groups; ++g) {
         Part &x = part[g];
-        x.rc = plan_rows_host(rb, re, M, p.seg_len, 0, skip_empty, pad, x.row_perm, x.heavy_rows, x.heavy_seg0, x.segs, &x.panel_len,
+        x.rc = plan_rows_host(rb, re, M, p.seg_len, reorder, skip_empty, pad, x.row_perm, x.heavy_rows, x.heavy_seg0, x.segs, &x.panel_len,
                               group_row[g], group_row[g + 1]);
         x.cost.resize(x.row_perm.size());
         for (size_t i = 0; i < x.row_perm.size(); ++i) {
@@ -326,8 +327,15 @@ static void plan_block_natural(const spmm_b200_handle *h, const int *rb, const i
         const int n = (int)x.row_perm.size();
         x.dst.resize((size_t)n);
         x.lpanel_len = pack_light_host(x.cost.data(), n, groups, steps, x.dst.data(), x.ltasks);
-        // light tasks and heavy segments merged by the row they start with
         x.utask.reserve(x.ltasks.size() + x.segs.size());
+        if (reorder) {
+            // degree buckets: the heavy segments (the longest rows) first, then the light tasks
+            for (size_t si = 0; si < x.segs.size(); ++si) x.utask.push_back(make_int2(-1 - (int)si, 0));
+            for (const int2 &t : x.ltasks) x.utask.push_back(t);
+            continue;
+        }
+        // natural order: light tasks and heavy segments merged by the row they start with, so that a heavy row runs next
+        // to its neighbours (whose B rows it shares in L2) instead of ahead of everything
         size_t li = 0, si = 0, first_i = 0;
         while (li < x.ltasks.size() || si < x.segs.size()) {
             int lrow = 0x7fffffff;
@@ -408,8 +416,8 @@ static void plan_block_host(const spmm_b200_handle *h, const int *rb, const int 
                             const int *group_row, int n_groups, HostBlock &hb) {
     const Plan &p = h->plan;
     const int M = h->num_v;
-    if (reorder == 0 && !p.scalar && group_row) {
-        plan_block_natural(h, rb, re, skip_empty, group_row, n_groups, hb);
+    if (!p.scalar && group_row) {
+        plan_block_groups(h, rb, re, skip_empty, reorder, group_row, n_groups, hb);
         return;
     }
     hb.reorder = reorder;
@@ -595,47 +603,28 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     auto row_begin = [&](int b) { return nb > 1 ? split.data() + (size_t)b * M : ptr.data(); };
     auto row_end = [&](int b) { return nb > 1 ? split.data() + (size_t)(b + 1) * M : ptr.data() + 1; };
 
-    // One persistent launch for all column blocks (option "persistent": 1 = always, 0 = one launch per block, -1 =
-    // automatic). Needs a single feature slice (K <= 256). Measured on B200 (profiles/r02_persistent.md), one rank's block
-    // of an N-way partition of the reddit shape, K = 256, against one launch per block: -1.4 % / -2.8 % / -4.2 % / -4.2 %
-    // at N = 2 / 3 / 4 / 6 (shortest block 28 / 19 / 14 / 9 waves of resident warps: the tail of every pass overlaps the
-    // next), +2 % at N = 1 (45 waves: nothing to gain, and the ticket bookkeeping costs a little) and +10 % at N = 8
-    // (7 waves: a task's completion is published during the warp's next task, and with passes this short the next
-    // pass's tasks of the same row group arrive before that and wait). Automatic = inside the window that pays.
-    bool persistent = !p.scalar && p.n_slices == 1 && nb <= kMaxBands && h->opt_persistent == 1;
-    if (!p.scalar && p.n_slices == 1 && nb > 1 && nb <= kMaxBands && h->opt_persistent < 0 && p.slots > 0) {
-        double shortest = 1e30;
-        for (int b = 0; b < nb; ++b) {
-            long long total = M;
-            const int *rb = row_begin(b), *re = row_end(b);
-            for (int r = 0; r < M; ++r) total += re[r] - rb[r];
-            const double tasks = (double)total / (total >= 64ll * p.slots * 64 ? 128 : 64);   // the automatic task sizes
-            shortest = std::min(shortest, tasks / (double)p.slots);
-        }
-        persistent = shortest >= 8.0 && shortest <= 36.0;
-    }
-    p.persistent = persistent;
-    // Row order per block, then row groups: in natural order the rows are cut into n_groups contiguous groups balanced by
-    // nonzeros; a task never spans a group, and a task of band b+1 waits for the tasks of band b that own its group.
-    // Bucketed order has no contiguous groups: one group (a band then waits for the whole band before it).
+    // Row order. Degree buckets (longest rows first) shorten the tail of every launch and keep the lanes of a task
+    // balanced; natural order keeps neighbouring rows together, which lets a graph's locality hit in L2. Natural order
+    // therefore only when locality is what is at stake: ONE block (no column blocks — B is either small or far larger than
+    // the L2) in a launch of at least 8 waves with a full warp per row: measured 12.2 -> 11.3 ms on the products shape and
+    // the opposite (0.14 -> 0.19 ms) on the one-wave arxiv shape (profiles/r01_sweep.md). With column blocks every pass
+    // gathers from an L2-resident band whatever the order, and buckets win at every partition size of the reddit shape
+    // (6.04 vs 6.14 ms whole, 0.80 vs 0.92 ms for a 1/8 block: profiles/r02_notes.md).
     std::vector<int> reorder(nb);
     bool all_natural = true;
-    if (p.persistent && h->opt_reorder < 0) {
-        // one launch over all blocks: its length is what decides between the two orders, not each block's own (the
-        // blocks of a rank's row partition are uneven — the block around the diagonal holds the graph's local half)
-        const long long total = (long long)h->num_e + (long long)M * nb;
-        const int r = (p.lanes == 32 && p.slots > 0 && total >= 8ll * p.slots * 64) ? 0 : 1;
-        for (int b = 0; b < nb; ++b) reorder[b] = r;
-        all_natural = r == 0;
-    } else {
-        for (int b = 0; b < nb; ++b) {
-            reorder[b] = block_reorder(h, row_begin(b), row_end(b));
-            all_natural &= reorder[b] == 0;
-        }
+    for (int b = 0; b < nb; ++b) {
+        reorder[b] = h->opt_reorder >= 0 ? (int)h->opt_reorder : (nb > 1 ? 1 : block_reorder(h, row_begin(b), row_end(b)));
+        all_natural &= reorder[b] == 0;
     }
-    p.n_groups = 1;
-    if (!p.scalar && all_natural) {
-        long long g = h->opt_row_groups > 0 ? h->opt_row_groups : 16;
+    // One persistent launch for all column blocks (option "persistent": 1 = on, needs a single feature slice; default off:
+    // built and parity-tested, but on the shapes measured the two-stream launches below do better — profiles/r02_notes.md).
+    p.persistent = !p.scalar && p.n_slices == 1 && nb <= kMaxBands && h->opt_persistent == 1;
+    // Row groups: contiguous row ranges balanced by nonzeros (the partition rule), planned independently (in parallel) and
+    // never spanned by a task. Natural order: 16. Degree buckets with several blocks: 2 — the halves that go out on two
+    // streams (below) and that order the passes inside a persistent launch. Otherwise 1.
+    {
+        long long g = h->opt_row_groups > 0 ? h->opt_row_groups : (all_natural ? 16 : (nb > 1 ? 2 : 1));
+        if (p.scalar) g = 1;
         if (g > kMaxRowGroups) g = kMaxRowGroups;
         if (g > M) g = M;
         p.n_groups = (int)g;
@@ -655,7 +644,7 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         // passes after the first skip rows without nonzeros in their band — except the last pass, which lists every
         // row: it is the one that delivers final rows (to C, to the stacked-layer targets, to run_host's host buffer)
         const bool skip_empty = b > 0 && b + 1 != nb;
-        plan_block_host(h, row_begin(b), row_end(b), skip_empty, reorder[b], all_natural ? p.group_row.data() : nullptr, p.n_groups, hb[b]);
+        plan_block_host(h, row_begin(b), row_end(b), skip_empty, reorder[b], p.group_row.data(), p.n_groups, hb[b]);
     }
     for (int b = 0; b < nb; ++b)
         if (hb[b].rc) {
@@ -710,6 +699,8 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         bp.n_ltask = (int)x.ltasks.size();
         bp.n_utask = (int)x.utask.size();
         bp.task_group = x.task_group;
+        // first task of the second half of the row groups (tasks are in row order, so the groups are contiguous)
+        bp.split_task = (int)(std::lower_bound(x.task_group.begin(), x.task_group.end(), (p.n_groups + 1) / 2) - x.task_group.begin());
         if ((rc = upload_vec(&bp.d_row_perm, x.row_perm, stream))) return rc;
         if ((rc = upload_vec(&bp.d_light_desc, x.light, stream))) return rc;
         if ((rc = upload_vec(&bp.d_utask, x.utask, stream))) return rc;
@@ -734,6 +725,15 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         heavy_off += (long long)x.heavy_rows.size();
     }
     tr.lap("uploads + panel kernels queued");
+
+    // Two-stream launches (option "split_streams": -1 auto = whenever there are several blocks and no persistent launch).
+    p.split_streams = !p.scalar && p.n_groups > 1 &&
+                      (h->opt_split_streams == 1 || (h->opt_split_streams < 0 && nb > 1 && !p.persistent));
+    if (p.split_streams && !h->aux_stream) {   // created here, not in run: run may be under CUDA-graph capture
+        SB_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
+    }
 
     // ---- the persistent launch's ticket list: band-major, absolute positions, row group and dependency per task ---------
     std::vector<int4> ptask;

@@ -844,7 +844,7 @@ void fill_band(BandArgs &b, const Plan &p, int blk) {
 
 }  // namespace
 
-int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
+int launch_spmm(spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t stream,
                 int *launches, const cudaEvent_t *band_ready, float *cfinal) {
     const Plan &p = h->plan;
     *launches = 0;
@@ -876,9 +876,26 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         SB_CUDA(cudaGetLastError());
         return 0;
     }
+    // Two-stream launches: every pass goes out as two kernels, the first half of the row groups on the caller's stream and
+    // the second half on a stream of the handle's. A pass only depends on the previous pass over the SAME rows, so each
+    // stream is its own chain, and while one kernel drains its last wave the other stream's kernel fills the freed SMs:
+    // the tail of every launch overlaps the next one without any synchronisation inside the kernels.
+    const bool two = p.split_streams && !p.scalar;
+    if (two) {
+        if (!h->aux_stream) {
+            SB_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+            SB_CUDA(cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
+        }
+        SB_CUDA(cudaEventRecord(h->aux_fork, stream));
+        SB_CUDA(cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+    }
     for (int blk = 0; blk < p.n_col_blocks; ++blk) {
         const BlockPlan &bp = p.blocks[blk];
-        if (band_ready) SB_CUDA(cudaStreamWaitEvent(stream, band_ready[blk], 0));
+        if (band_ready) {
+            SB_CUDA(cudaStreamWaitEvent(stream, band_ready[blk], 0));
+            if (two) SB_CUDA(cudaStreamWaitEvent(h->aux_stream, band_ready[blk], 0));
+        }
         if (bp.n_light == 0 && bp.n_seg == 0) continue;
         RunArgs a;
         fill_common(a.c, h, vin, vout, cfinal);
@@ -886,11 +903,24 @@ int launch_spmm(const spmm_b200_handle *h, const float *vin, float *vout, cudaSt
         if (p.scalar) {
             const int warps = p.block / 32;
             spmm_scalar_kernel<<<(unsigned)((a.b.n_light + warps - 1) / warps), p.block, 0, stream>>>(a);
-        } else {
-            int rc = launch_lanes(p, a, full, stream);
-            if (rc) return rc;
+            ++*launches;
+            continue;
         }
-        ++*launches;
+        const int n = bp.n_utask, cut = two ? bp.split_task : n;
+        for (int half = 0; half < 2; ++half) {
+            const int t0 = half ? cut : 0, t1 = half ? n : cut;
+            if (t1 <= t0) continue;
+            RunArgs b = a;
+            b.b.utask = a.b.utask + t0;
+            b.b.n_utask = t1 - t0;
+            int rc = launch_lanes(p, b, full, half ? h->aux_stream : stream);
+            if (rc) return rc;
+            ++*launches;
+        }
+    }
+    if (two) {
+        SB_CUDA(cudaEventRecord(h->aux_join, h->aux_stream));
+        SB_CUDA(cudaStreamWaitEvent(stream, h->aux_join, 0));
     }
     SB_CUDA(cudaGetLastError());
     return 0;

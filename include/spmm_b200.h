@@ -43,18 +43,23 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *   "seg_len"   nonzeros per heavy-row segment; rows longer than this are split (0 = auto)
  *   "kslice"    feature columns per pass over the graph (0 = auto; else multiple of 4)
  *   "block"     threads per CTA (multiple of 32)
- *   "reorder"   1 = degree-bucketed row order, 0 = natural order, -1 (default) = natural when a full warp
- *               serves each row (K >= 128) and the graph is at least 8 waves of tasks long, else bucketed
+ *   "reorder"   1 = degree-bucketed row order, 0 = natural order, -1 (default) = natural for single-block plans when a
+ *               full warp serves each row (K >= 128) and the graph is at least 8 waves of tasks long, else bucketed
  *   "light_steps" entries per lane group and stream task (0 = auto: 64 / groups, at least 16;
  *               128 on very large graphs at K >= 128; smaller on graphs of fewer than 4 waves of tasks, to
  *               fill whole waves of resident warps)
  *   "col_blocks" passes over A, each gathering from one band of B rows that fits the L2
  *               (0 = auto: 1 unless B is larger than the L2 and rows are long); needs ascending
  *               columns inside each row, otherwise falls back to 1
- *   "persistent" -1 (default) = run() is one persistent launch whenever the plan has several column blocks (a grid of
- *               co-resident warps draws tasks from a counter; band b+1's tasks wait for band b's tasks of the same row
- *               group), 1 = also for a single block, 0 = one launch per column block. Needs feat_in <= 256.
- *   "row_groups" row groups of the persistent launch (0 = auto: 16 in natural row order, else 1; at most 64)
+ *   "split_streams" -1 (default) = with several column blocks every pass goes out as two launches, the two halves of
+ *               the rows, on two streams (each tail overlaps the next launch), 0 = one launch per column block, 1 = on
+ *   "persistent" 1 = run() is one persistent launch over all column blocks (a grid of co-resident warps draws tasks from
+ *               a counter; band b+1's tasks wait for band b's tasks of the same row group). Needs feat_in <= 256.
+ *               Default off: measured slower than the two-stream launches (profiles/r02_notes.md)
+ *   "row_groups" contiguous row groups, balanced by nonzeros, that no task spans (0 = auto: 16 in natural row order, 2
+ *               in bucketed order with several column blocks, else 1; at most 64): the unit of parallel planning, of the
+ *               two-stream launches and of the persistent launch's dependencies
+ *   "ticket_batch" persistent launch: tickets drawn per atomic while far from the end (0 = auto)
  *   "zero_copy" run_host / run_host_sharded: 1 (default) = when the output buffer is pinned host memory the last pass
  *               stores final rows straight into it (no separate device-to-host copy), 0 = always copy
  *   "tune"      measured kernel variant, 0 (default) or 1, see hpc_b200/csrc/spmm_kernels.cu

@@ -87,18 +87,27 @@ def split_rows(ptr, idx, nb: int, b_rows: int) -> np.ndarray:
     return out.astype(np.int32)
 
 
+def row_groups_of(m: int, group_row) -> np.ndarray:
+    """Row group of every row: group g owns rows [group_row[g], group_row[g+1]); one group when group_row is None."""
+    if group_row is None:
+        return np.zeros(m, np.int64)
+    return np.searchsorted(np.asarray(group_row, np.int64), np.arange(m, dtype=np.int64), side="right") - 1
+
+
 def plan(ptr, idx, val, seg_len: int, reorder: bool = True, rb=None, re=None, skip_empty: bool = False, k4: int = 1,
-         pad: int = 2) -> dict:
+         pad: int = 2, group_row=None) -> dict:
     """Plan of the whole matrix (rb/re omitted) or of one column block (row r owns [rb[r], re[r])).
     k4 = feat // 4: panels store a column as the B row's offset in float4 units (col * k4).
-    pad = 4 * (32 // lanes): every segment's span is padded with nop entries (-1, 0) to a multiple of it."""
+    pad = 4 * (32 // lanes): every segment's span is padded with nop entries (-1, 0) to a multiple of it.
+    group_row: row-group bounds; the row order (degree buckets or natural) applies inside each group, groups in order."""
     ptr = np.asarray(ptr, np.int64)
     m = len(ptr) - 1
     rb = ptr[:-1] if rb is None else np.asarray(rb, np.int64)
     re = ptr[1:] if re is None else np.asarray(re, np.int64)
     deg = re - rb
     if reorder:
-        order = np.argsort(-bit_length(deg), kind="stable")
+        # by (row group, degree bucket descending, row): lexsort's last key is the primary one
+        order = np.lexsort((np.arange(m), -bit_length(deg), row_groups_of(m, group_row)))
     else:
         order = np.arange(m)
     if skip_empty:
@@ -198,7 +207,8 @@ def light_stream(plan_dict, idx, val, groups: int, steps: int, k4: int = 1, grou
     """light_desc with header slots, task list and the stream panel for a plan() result. group_row: the row-group
     bounds of the persistent launch (natural row order): no task spans a bound."""
     ld = plan_dict["light_desc"].copy()
-    cuts = () if group_row is None else [int(np.searchsorted(ld[:, 0], r, side="left")) for r in group_row[1:-1]]
+    grp = row_groups_of(int(ld[:, 0].max()) + 1 if len(ld) else 0, group_row)[ld[:, 0]] if len(ld) else np.zeros(0, np.int64)
+    cuts = [i for i in range(1, len(ld)) if grp[i] != grp[i - 1]]     # the light rows are group-major in either order
     dst, tasks, length = pack_light(ld[:, 2].astype(np.int64) + 1, groups, steps, cuts)
     ld[:, 3] = dst
     panel = np.full((length, 2), -1, np.int32)
@@ -213,18 +223,23 @@ def light_stream(plan_dict, idx, val, groups: int, steps: int, k4: int = 1, grou
     return {"light_desc": ld, "ltask": tasks, "lpanel": panel}
 
 
-def unified_tasks(plan_dict, stream_dict, reorder: bool) -> np.ndarray:
+def unified_tasks(plan_dict, stream_dict, reorder: bool, group_row=None) -> np.ndarray:
     """Scheduling order of the warp tasks of one slice: (lpanel offset, steps) for a light task, (-1 - segment, 0) for
-    a heavy segment. Bucketed rows: all segments, then the light tasks. Natural order: merged by first row (a light
-    task's first row is the row whose header sits at its offset)."""
+    a heavy segment. Bucketed rows: per row group, all its segments, then its light tasks. Natural order: merged by
+    first row (a light task's first row is the row whose header sits at its offset)."""
     ltask = stream_dict["ltask"]
     nseg = len(plan_dict["seg_desc"])
     heavy = [(-1 - s, 0) for s in range(nseg)]
     light = [tuple(int(x) for x in t) for t in ltask]
-    if reorder:
-        return np.asarray(heavy + light, np.int32).reshape(-1, 2)
     ld = stream_dict["light_desc"]
     first_row = {int(d): int(r) for r, _, _, d in ld}          # header slot -> row
+    if reorder:
+        gr = np.asarray([0, 1 << 62] if group_row is None else group_row, np.int64)
+        grp_of = lambda row: int(np.searchsorted(gr, row, side="right")) - 1
+        keyed = [(grp_of(int(plan_dict["seg_desc"][s][0])), 0, s, heavy[s]) for s in range(nseg)] + \
+                [(grp_of(first_row[t[0]]), 1, i, t) for i, t in enumerate(light)]
+        keyed.sort(key=lambda k: k[:3])
+        return np.asarray([k[3] for k in keyed], np.int32).reshape(-1, 2)
     keyed = [(first_row[t[0]], 1, t) for t in light] + [(int(plan_dict["seg_desc"][s][0]), 0, heavy[s]) for s in range(nseg)]
     keyed.sort(key=lambda k: (k[0], k[1]))                     # stable: a row's segments stay in order
     return np.asarray([k[2] for k in keyed], np.int32).reshape(-1, 2)

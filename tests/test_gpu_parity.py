@@ -352,7 +352,8 @@ def test_run_host_matches_device_run(opts):
         op.run_host(h_in, h_out)
         assert np.array_equal(h_out.numpy().view(np.int32), got.ravel().view(np.int32))
     info = op.plan_info()
-    assert op.run_profiled(vin, vout) > 0 and op.launches_per_run == (1 if info["persistent"] else info["n_col_blocks"])
+    want = 1 if info["persistent"] else info["n_col_blocks"] * (2 if info["n_col_blocks"] > 1 else 1)   # row halves on two streams
+    assert op.run_profiled(vin, vout) > 0 and op.launches_per_run == want
     op.close()
 
 
@@ -404,10 +405,15 @@ def test_column_block_plan_matches_oracle(shape, K, nb, seg_len):
         inf = op.plan_info(b)
         assert (inf["col_begin"], inf["col_end"]) == (b * cpb, min(M, (b + 1) * cpb))
         assert np.array_equal(got["split"], split)
+        # several column blocks, degree buckets: two row groups (the halves that go out on two streams), buckets inside each
+        assert inf["n_row_groups"] == 2 and inf["reorder"] == 1
+        group_row = P.partition_rows(ptr, 2)
+        assert np.array_equal(got["group_row"], group_row)
         want = P.plan(ptr, idx, val, inf["seg_len"], True, rb=split[b], re=split[b + 1], skip_empty=0 < b < nb - 1, k4=K // 4,
-                      pad=4 * (32 // inf["lanes"]))
-        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"], k4=K // 4))
-        for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel"):
+                      pad=4 * (32 // inf["lanes"]), group_row=group_row)
+        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"], k4=K // 4, group_row=group_row))
+        want["utask"] = P.unified_tasks(want, want, True, group_row)
+        for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel", "utask"):
             assert np.array_equal(got[k], want[k]), (b, k)
         # every nonzero of the block lies in its band of B rows
         for r0, beg, d, _ in got["light_desc"][:200]:
@@ -424,19 +430,18 @@ def test_column_block_plan_matches_oracle(shape, K, nb, seg_len):
     op.close()
 
 
-@pytest.mark.parametrize("shape,K,nb,seg_len,groups", [("c0", 256, 3, 32, 4), ("arxiv", 256, 4, 0, 16), ("c0", 32, 3, 16, 1),
-                                                       ("c0", 128, 1, 64, 0)])
-def test_persistent_plan_matches_oracle(shape, K, nb, seg_len, groups):
+@pytest.mark.parametrize("shape,K,nb,seg_len,groups,natural", [("c0", 256, 3, 32, 4, True), ("arxiv", 256, 4, 0, 16, True), ("c0", 32, 3, 16, 1, False),
+                                                               ("c0", 128, 1, 64, 0, True), ("c0", 64, 3, 16, 0, False), ("arxiv", 256, 5, 0, 3, False)])
+def test_persistent_plan_matches_oracle(shape, K, nb, seg_len, groups, natural):
     """The single persistent launch: row groups, tasks cut at group bounds, band-major ticket list with dependency
     counts — every array against the numpy restatement (oracle/plan_oracle.py::ticket_list)."""
     ptr, idx = H.gen_named_graph(shape)
     g, vin, vout = dev_inputs(ptr, idx, K)
-    natural = groups != 1
     op = H.SpMMB200(g, K, col_blocks=nb, seg_len=seg_len, reorder=0 if natural else 1, persistent=1, row_groups=groups)
     op.preprocess(vin, vout)
     info = op.plan_info(0)
     assert info["persistent"] == 1 and info["n_col_blocks"] == nb
-    want_groups = (groups or 16) if natural else 1
+    want_groups = groups or (16 if natural else (2 if nb > 1 else 1))
     assert info["n_row_groups"] == want_groups
     M = g.num_v
     val = g.val.cpu().numpy()
@@ -449,10 +454,9 @@ def test_persistent_plan_matches_oracle(shape, K, nb, seg_len, groups):
         if b == 0:
             assert np.array_equal(got["group_row"], group_row)
         want = P.plan(ptr, idx, val, inf["seg_len"], not natural, rb=split[b], re=split[b + 1], skip_empty=0 < b < nb - 1, k4=K // 4,
-                      pad=4 * (32 // inf["lanes"]))
-        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"], k4=K // 4,
-                                   group_row=group_row if want_groups > 1 else None))
-        want["utask"] = P.unified_tasks(want, want, not natural)
+                      pad=4 * (32 // inf["lanes"]), group_row=group_row)
+        want.update(P.light_stream(want, idx, val, 32 // inf["lanes"], inf["light_steps"], k4=K // 4, group_row=group_row))
+        want["utask"] = P.unified_tasks(want, want, not natural, group_row)
         for k in ("row_perm", "light_desc", "ltask", "lpanel", "heavy_rows", "heavy_seg0", "seg_desc", "seg_hrow", "panel", "utask"):
             assert np.array_equal(got[k], want[k]), (b, k)
         blocks.append((want["utask"], want["light_desc"], want["seg_desc"], len(want["lpanel"]), len(want["panel"])))
@@ -486,7 +490,8 @@ def test_unsorted_columns_fall_back_to_one_block():
 
 
 def test_auto_row_order_rule():
-    """Small graphs keep degree buckets; many-wave graphs at K >= 128 use natural order (plan_info reports it)."""
+    """Small graphs keep degree buckets; many-wave single-block graphs at K >= 128 use natural order; with column blocks
+    (every pass gathers from an L2-resident band whatever the order) buckets again (plan_info reports it)."""
     ptr, idx = H.gen_named_graph("arxiv")
     g, vin, vout = dev_inputs(ptr, idx, 256)
     op = H.SpMMB200(g, 256)
@@ -496,6 +501,16 @@ def test_auto_row_order_rule():
     assert info["reorder"] == int(P.auto_reorder(info["lanes"], total, info["resident_warps"])) == 1
     assert P.auto_reorder(32, 126_000_000, info["resident_warps"]) is False
     assert P.auto_reorder(8, 126_000_000, info["resident_warps"]) is True
+    op.close()
+    op = H.SpMMB200(g, 256, col_blocks=3)
+    op.preprocess(vin, vout)
+    info = op.plan_info()
+    assert info["reorder"] == 1 and info["n_row_groups"] == 2 and info["persistent"] == 0
+    vout.fill_(float("nan"))
+    op.run(vin, vout)
+    torch.cuda.synchronize()
+    assert op.launches_per_run == 6          # three passes, each as two launches (row halves) on two streams
+    check_against_oracle(ptr, idx, 256, op, g, vin, vout[: g.num_v * 256].cpu().numpy().reshape(g.num_v, 256))
     op.close()
 
 
@@ -936,12 +951,13 @@ def test_reference_test_driver_with_engine_dropped_in(tmp_path, shape, K):
     assert len(times) == 2 and all(t > 0 for t in times)          # cuSPARSE, then the engine (test_spmm.cu:46-62)
 
 
-def test_run_is_capturable_in_a_cuda_graph():
-    """run() makes no host synchronisation, so a launch-bound caller can capture it once and replay it."""
+@pytest.mark.parametrize("K,opts", [(32, {}), (64, {"col_blocks": 3}), (64, {"col_blocks": 3, "persistent": 1})])
+def test_run_is_capturable_in_a_cuda_graph(K, opts):
+    """run() makes no host synchronisation, so a launch-bound caller can capture it once and replay it — also when the
+    passes go out on two streams (fork / join inside the capture) and as the one persistent launch."""
     ptr, idx = H.gen_named_graph("arxiv")
-    K = 32
     g, vin, vout = dev_inputs(ptr, idx, K)
-    op = H.SpMMB200(g, K)
+    op = H.SpMMB200(g, K, **opts)
     op.preprocess(vin, vout)
     op.run(vin, vout)
     torch.cuda.synchronize()

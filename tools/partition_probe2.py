@@ -18,12 +18,13 @@ for parts in (1, 2, 3, 4, 6, 8):
     g = H.CSR(r1 - r0, e1 - e0, torch.from_numpy(lptr).cuda(), d_idx[e0:e1].clone(), val[e0:e1].clone())
     vout = torch.empty((r1 - r0) * K, device="cuda")
     ops = {}
-    for name, opts in (("multi", {"persistent": 0}), ("persistent", {"persistent": 1})):
+    for name, opts in (("multi", {"persistent": 0, "split_streams": 0}), ("persistent", {"persistent": 1}),
+                       ("split", {"persistent": 0, "split_streams": 1})):
         op = H.SpMMB200(g, K, b_rows=M, **opts)
         op.preprocess(vin, vout)
         for _ in range(5): op.run(vin, vout)
         ops[name] = op
-    res = {"multi": [], "persistent": []}
+    res = {"multi": [], "persistent": [], "split": []}
     for rep in range(4):
         for name, op in ops.items():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,9 +32,19 @@ for parts in (1, 2, 3, 4, 6, 8):
             for _ in range(20): op.run(vin, vout)
             b.record(); torch.cuda.synchronize()
             res[name].append(a.elapsed_time(b) / 20)
+    outs = []
+    for name, op in ops.items():
+        o = torch.full_like(vout, float("nan"))
+        op.run(vin, o)
+        torch.cuda.synchronize()
+        outs.append(o)
+    eq = all(torch.equal(outs[0], o) for o in outs[1:])
     info = ops["persistent"].plan_info()
     bands = [ops["multi"].plan_info(b)["n_utask"] for b in range(info["n_col_blocks"])]
     print(json.dumps({"parts": parts, "band_tasks": bands, "waves_shortest_band": round(min(bands) / info["resident_warps"], 1),
                       "ms_multi": [round(x, 4) for x in res["multi"]], "ms_persistent": [round(x, 4) for x in res["persistent"]],
-                      "ratio": round(float(np.mean(res["persistent"]) / np.mean(res["multi"])), 4)}), flush=True)
+                      "ms_split": [round(x, 4) for x in res["split"]],
+                      "ratio_persistent": round(float(np.mean(res["persistent"]) / np.mean(res["multi"])), 4),
+                      "ratio_split": round(float(np.mean(res["split"]) / np.mean(res["multi"])), 4),
+                      "bit_equal": bool(eq)}), flush=True)
     for op in ops.values(): op.close()
