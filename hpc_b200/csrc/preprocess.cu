@@ -639,7 +639,8 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
 
     // ---- host planning of every block (independent of each other) -------------------------------------------------
     std::vector<HostBlock> hb((size_t)nb);
-    // (the row groups inside a block are planned in parallel; the blocks one after the other)
+    // (several blocks: one host thread per block; a single block: its row groups in parallel — nested regions stay serial)
+#pragma omp parallel for schedule(dynamic, 1) if (nb > 1)
     for (int b = 0; b < nb; ++b) {
         // passes after the first skip rows without nonzeros in their band — except the last pass, which lists every
         // row: it is the one that delivers final rows (to C, to the stacked-layer targets, to run_host's host buffer)
