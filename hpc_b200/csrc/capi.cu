@@ -85,6 +85,7 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value) {
     else if (!strcmp(name, "row_groups") && value >= 0 && value <= kMaxRowGroups) h->opt_row_groups = value;
     else if (!strcmp(name, "ticket_batch") && value >= 0 && value <= 16) h->opt_ticket_batch = value;
     else if (!strcmp(name, "split_streams") && value >= -1 && value <= 1) h->opt_split_streams = value;
+    else if (!strcmp(name, "host_bands") && (value == 0 || value == 1 || (value >= 10 && value <= 90))) h->opt_host_bands = value;
     else if (!strcmp(name, "zero_copy") && value >= 0 && value <= 1) {
         h->opt_zero_copy = value;   // run_host only; not part of the plan
         return 0;

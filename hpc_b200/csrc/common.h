@@ -156,7 +156,7 @@ struct spmm_b200_handle {
     const float *d_val = nullptr;
     int num_v = 0, num_e = 0, feat = 0;
     long long opt_seg_len = 0, opt_kslice = 0, opt_block = 128, opt_reorder = -1, opt_tune = 0, opt_col_blocks = 0, opt_light_steps = 0,
-              opt_zero_copy = 1, opt_persistent = -1, opt_row_groups = 0, opt_ticket_batch = 0, opt_split_streams = -1;
+              opt_zero_copy = 1, opt_persistent = -1, opt_row_groups = 0, opt_ticket_batch = 0, opt_split_streams = -1, opt_host_bands = 0;
     int plan_select = 0;   // which column block plan_info / plan_copy describe
     spmm_b200::Plan plan;
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
@@ -203,7 +203,9 @@ int launch_spmm(spmm_b200_handle *h, const float *vin, float *vout, cudaStream_t
 int resident_warps(int lanes, int vec, int tune, int block);
 int persistent_grid(int lanes, int vec, int tune, int block);   // CTAs that are co-resident for the persistent kernel
 int launch_check_cols(const int *d_idx, long long nnz, int b_rows, int *d_bad, cudaStream_t stream);
-int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
+// band_begin[0..n_col_blocks]: first B row of every column block (band_begin[n] = b_rows), at most kMaxSplitBands blocks
+constexpr int kMaxSplitBands = 64;
+int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, const int *band_begin,
                       int *d_split, int *d_unsorted, cudaStream_t stream);
 int launch_build_lpanel(const int4 *d_light_desc, int n_light, int groups, int k4, const int *d_idx, const float *d_val,
                         int2 *d_lpanel, cudaStream_t stream);

@@ -570,12 +570,32 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     // split every row at the column-block boundaries (needs ascending columns inside a row; a graph
     // that is not sorted falls back to a single block)
     std::vector<int> split;
-    int cols_per_block = nb > 1 ? (b_rows + nb - 1) / nb : b_rows;
-    if (nb > 1) nb = (b_rows + cols_per_block - 1) / cols_per_block;   // every band starts inside B (b_rows = 10, 7 bands -> 5 of 2 rows)
+    // Band bounds. Default: nb equal bands of ceil(b_rows / nb) rows. Option "host_bands" (the plan is meant for the
+    // host-buffer call, spmm_b200_run_host): the LAST band takes the last 40 % of B's rows and the bands before it share
+    // the rest. The last pass stores final rows over PCIe and is bound by that transfer whatever it computes, so it may
+    // as well carry half of the nonzeros (from a band that no longer fits the L2), while the small early bands let the
+    // first pass start sooner and finish the rest of the work under the upload of B.
+    std::vector<int> band_begin;
+    if (nb > 1 && h->opt_host_bands && nb >= 3) {
+        // host_bands = 1: the last band is 40 % of B's rows (measured best on the reddit shape: e2e 10.31 -> 9.34 ms;
+        // 30 %: 9.76, 50 %: 9.60, 60 %: 9.98 — profiles/r02_host_bands.jsonl); 10..90: that percentage
+        const long long pct = h->opt_host_bands >= 10 ? h->opt_host_bands : 40;
+        const int small = nb - 1, half = (int)((long long)b_rows * (100 - pct) / 100);
+        const int per = (half + small - 1) / small;
+        for (int b = 0; b < small && b * per < half; ++b) band_begin.push_back(b * per);
+        band_begin.push_back(half);
+        band_begin.push_back(b_rows);
+        nb = (int)band_begin.size() - 1;
+    } else {
+        const int cols_per_block = nb > 1 ? (b_rows + nb - 1) / nb : b_rows;
+        if (nb > 1) nb = (b_rows + cols_per_block - 1) / cols_per_block;   // every band starts inside B (b_rows = 10, 7 bands -> 5 of 2 rows)
+        for (int b = 0; b < nb; ++b) band_begin.push_back(b * cols_per_block);
+        band_begin.push_back(b_rows);
+    }
     if (nb > 1) {
         if (cudaMalloc((void **)&p.d_split, sizeof(int) * (size_t)(nb + 1) * M) != cudaSuccess)
             return with_flags(cuda_fail(cudaGetLastError(), "cudaMalloc(split)", __FILE__, __LINE__));
-        rc = launch_split_rows(h->d_ptr, h->d_idx, M, nb, cols_per_block, p.d_split, d_flags + 1, stream);
+        rc = launch_split_rows(h->d_ptr, h->d_idx, M, nb, band_begin.data(), p.d_split, d_flags + 1, stream);
         if (rc) return with_flags(rc);
         split.resize((size_t)(nb + 1) * M);
         cudaError_t e = cudaMemcpyAsync(split.data(), p.d_split, sizeof(int) * split.size(), cudaMemcpyDeviceToHost, stream);
@@ -687,8 +707,8 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
     for (int b = 0; b < nb; ++b) {
         BlockPlan &bp = p.blocks[b];
         HostBlock &x = hb[b];
-        bp.col_begin = nb > 1 ? b * cols_per_block : 0;
-        bp.col_end = nb > 1 ? (b + 1 == nb ? b_rows : (b + 1) * cols_per_block) : b_rows;
+        bp.col_begin = nb > 1 ? band_begin[b] : 0;
+        bp.col_end = nb > 1 ? band_begin[b + 1] : b_rows;
         bp.reorder = x.reorder;
         bp.light_steps = x.light_steps;
         if (b == 0 && h->opt_light_steps <= 0) p.light_steps = x.light_steps;   // reported by plan_info (block 0)

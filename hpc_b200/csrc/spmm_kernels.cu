@@ -624,8 +624,11 @@ __global__ void __launch_bounds__(256) spmm_scalar_kernel(const __grid_constant_
 
 // one warp per row: position of every column-block boundary inside the row (binary search by lane b),
 // and a check that the row's columns ascend (otherwise the blocks are not contiguous)
+struct BandBounds {
+    int begin[kMaxSplitBands + 1];
+};
 __global__ void __launch_bounds__(256) split_rows_kernel(const int *ptr, const int *idx, int num_v, int nb,
-                                                         int cols_per_block, int *split, int *unsorted) {
+                                                         const BandBounds bands, int *split, int *unsorted) {
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= num_v) return;
@@ -638,7 +641,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const int *ptr, const i
         if (b == 0) pos = begin;
         else if (b == nb) pos = end;
         else {
-            const int target = b * cols_per_block;   // first position with idx >= target
+            const int target = bands.begin[b];   // first position with idx >= target
             int lo = begin, hi = end;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -954,12 +957,18 @@ int launch_check_cols(const int *d_idx, long long nnz, int b_rows, int *d_bad, c
     return 0;
 }
 
-int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, int cols_per_block,
+int launch_split_rows(const int *d_ptr, const int *d_idx, int num_v, int n_col_blocks, const int *band_begin,
                       int *d_split, int *d_unsorted, cudaStream_t stream) {
     if (num_v == 0) return 0;
+    if (n_col_blocks > kMaxSplitBands) {
+        set_error("too many column blocks: %d > %d", n_col_blocks, kMaxSplitBands);
+        return SPMM_B200_EINVAL;
+    }
+    BandBounds bands;
+    for (int b = 0; b <= kMaxSplitBands; ++b) bands.begin[b] = band_begin[b < n_col_blocks ? b : n_col_blocks];
     const long long threads = (long long)num_v * 32;
-    split_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_ptr, d_idx, num_v, n_col_blocks,
-                                                                            cols_per_block, d_split, d_unsorted);
+    split_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_ptr, d_idx, num_v, n_col_blocks, bands, d_split,
+                                                                            d_unsorted);
     SB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -60,6 +60,11 @@ int spmm_b200_set_feat(spmm_b200_t h, int feat_in);
  *               in bucketed order with several column blocks, else 1; at most 64): the unit of parallel planning, of the
  *               two-stream launches and of the persistent launch's dependencies
  *   "ticket_batch" persistent launch: tickets drawn per atomic while far from the end (0 = auto)
+ *   "host_bands" 1 = lay the column blocks out for spmm_b200_run_host: the last block takes the last 40 % of B's rows
+ *               (its pass is bound by the PCIe transfer of C anyway), the blocks before it share the rest (the first
+ *               pass starts sooner, the rest finishes under the upload of B); 10..90 = that percentage instead of 40.
+ *               0 (default) = equal blocks, best for run(). Rows split into segments sum in a different association
+ *               than with equal blocks (same tolerance); whole rows stay bit-exact
  *   "zero_copy" run_host / run_host_sharded: 1 (default) = when the output buffer is pinned host memory the last pass
  *               stores final rows straight into it (no separate device-to-host copy), 0 = always copy
  *   "tune"      measured kernel variant, 0 (default) or 1, see hpc_b200/csrc/spmm_kernels.cu

@@ -70,20 +70,29 @@ def auto_col_blocks(b_rows: int, feat: int, nnz: int, num_v: int) -> int:
     return nb
 
 
-def split_rows(ptr, idx, nb: int, b_rows: int) -> np.ndarray:
-    """split[b, r] = first CSR position of row r whose column is >= b * ceil(b_rows / nb)
-    (split[0] = ptr[r], split[nb] = ptr[r+1]); columns must ascend inside a row."""
+def host_band_bounds(nb: int, b_rows: int, pct: int = 40):
+    """Option host_bands: the last band is the last pct % of B's rows, the nb - 1 bands before it share the rest."""
+    small, half = nb - 1, b_rows * (100 - pct) // 100
+    per = -(-half // small)
+    return [b * per for b in range(small) if b * per < half] + [half, b_rows]
+
+
+def split_rows(ptr, idx, nb: int, b_rows: int, bounds=None) -> np.ndarray:
+    """split[b, r] = first CSR position of row r whose column is >= the first B row of band b — b * ceil(b_rows / nb),
+    or bounds[b] — (split[0] = ptr[r], split[nb] = ptr[r+1]); columns must ascend inside a row."""
     ptr = np.asarray(ptr, np.int64)
     idx = np.asarray(idx, np.int64)
     m = len(ptr) - 1
     cpb = -(-b_rows // nb)
+    if bounds is None:
+        bounds = [b * cpb for b in range(nb)]
     # rank of (row, column) pairs in the row-major, column-ascending order the CSR already has
     row_of = np.repeat(np.arange(m, dtype=np.int64), np.diff(ptr))
     keys = row_of * (b_rows + 1) + idx
     out = np.empty((nb + 1, m), np.int64)
     out[0], out[nb] = ptr[:-1], ptr[1:]
     for b in range(1, nb):
-        out[b] = np.searchsorted(keys, np.arange(m, dtype=np.int64) * (b_rows + 1) + b * cpb, side="left")
+        out[b] = np.searchsorted(keys, np.arange(m, dtype=np.int64) * (b_rows + 1) + bounds[b], side="left")
     return out.astype(np.int32)
 
 

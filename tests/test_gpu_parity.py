@@ -666,6 +666,30 @@ def test_full_output_against_reference_kernel_k256(shape):
     op.close()
 
 
+def test_host_bands_layout_for_run_host():
+    """Option host_bands: the last column block is the last 40 % of B (its pass is bound by the PCIe transfer of C), the
+    blocks before it share the rest. Bounds and row splits against the oracle; result unchanged; run_host bit-equal."""
+    ptr, idx = H.gen_named_graph("c0")
+    K, nb = 64, 4
+    op, g, vin, vout, got = run_engine(ptr, idx, K, col_blocks=nb, host_bands=1, seg_len=32)
+    M = g.num_v
+    bounds = P.host_band_bounds(nb, M)
+    assert bounds == [0, 819, 1638, 2457, 4096]
+    info = op.plan_info()
+    assert info["n_col_blocks"] == nb
+    split = P.split_rows(ptr, idx, nb, M, bounds=bounds)
+    for b in range(nb):
+        inf = op.plan_info(b)
+        assert (inf["col_begin"], inf["col_end"]) == (bounds[b], bounds[b + 1])
+    assert np.array_equal(op.plan_arrays(0)["split"], split)
+    check_against_oracle(ptr, idx, K, op, g, vin, got)
+    h_in, h_out = vin.cpu().pin_memory(), torch.full((M * K,), float("nan")).pin_memory()
+    for _ in range(2):
+        op.run_host(h_in, h_out)
+        assert np.array_equal(h_out.numpy().view(np.int32), got.ravel().view(np.int32))
+    op.close()
+
+
 def test_refresh_values_after_in_place_update():
     """The plan snapshots idx/val into its panels (spmm_b200.h: SNAPSHOT); refresh_values re-stages them without a new
     plan. The reference's SpMMOpt::run reads idx/val live (PA4/workspace/src/spmm_opt.cu:22-25)."""
