@@ -184,7 +184,7 @@ int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin, float *h_vout,
     if ((rc = launch_xrank_barrier(h->rep_flags, world, rank, 0, call, c))) return rc;
     long long h2d = 0;
     for (int ck = 0; ck < n_chunks; ++ck) {
-        const long long c0 = (long long)ck * chunk_rows, c1 = std::min<long long>(b_rows, c0 + chunk_rows);
+        const long long c0 = std::min<long long>(b_rows, (long long)ck * chunk_rows), c1 = std::min<long long>(b_rows, c0 + chunk_rows);
         const long long r0 = c0 + (c1 - c0) * rank / world, r1 = c0 + (c1 - c0) * (rank + 1) / world;
         const long long off = r0 * h->feat, cnt = (r1 - r0) * h->feat;
         if (cnt) {
