@@ -6,6 +6,9 @@
 // `multimem.st` per 16 bytes through the NVLS multicast address when there is one, else one `st.global` per peer —
 // and a device-side flag barrier over the same peer mappings orders the pushes against the SpMM passes. PCIe then
 // carries 4·b_rows·K/N bytes in and 4·rows_g·K bytes out per rank instead of the whole B on every rank.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -176,12 +179,22 @@ int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin, float *h_vout,
     float *local_b = h->rep_b[rank];
     cudaStream_t c = h->copy_stream;
     int rc;
+    // SPMM_B200_TRACE_HOST=1: device timestamps of the call's phases on stderr (rank 0 and the last rank)
+    static const bool trace = getenv("SPMM_B200_TRACE_HOST") != nullptr;
+    cudaEvent_t tev[24] = {nullptr};
+    int n_tev = 0;
+    auto stamp = [&](cudaStream_t st) {
+        if (!trace || n_tev >= 24) return;
+        if (cudaEventCreate(&tev[n_tev]) == cudaSuccess) cudaEventRecord(tev[n_tev++], st);
+    };
+    stamp(s);
     // the copy stream starts behind whatever is queued on the caller's stream (the previous call's passes)
     SB_CUDA(cudaEventRecord(h->band_events[n_chunks], s));
     SB_CUDA(cudaStreamWaitEvent(c, h->band_events[n_chunks], 0));
     // phase 0: every rank is done gathering from its copy of B (previous call) before anybody overwrites a row of it
     const unsigned int call = ++h->rep_epoch;
     if ((rc = launch_xrank_barrier(h->rep_flags, world, rank, 0, call, c))) return rc;
+    stamp(c);
     long long h2d = 0;
     for (int ck = 0; ck < n_chunks; ++ck) {
         const long long c0 = std::min<long long>(b_rows, (long long)ck * chunk_rows), c1 = std::min<long long>(b_rows, c0 + chunk_rows);
@@ -194,8 +207,10 @@ int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin, float *h_vout,
         }
         // phase 1, one epoch per chunk: every rank's piece of this chunk has landed everywhere
         const unsigned int epoch = (call - 1) * (unsigned int)n_chunks + (unsigned int)ck + 1u;
+        stamp(c);
         if ((rc = launch_xrank_barrier(h->rep_flags, world, rank, 1, epoch, c))) return rc;
         SB_CUDA(cudaEventRecord(h->band_events[ck], c));
+        stamp(c);
     }
     h->rep_h2d_bytes = h2d;
     if (n) {
@@ -211,8 +226,21 @@ int spmm_b200_run_host_sharded(spmm_b200_t h, const float *h_vin, float *h_vout,
     } else {
         SB_CUDA(cudaStreamWaitEvent(s, h->band_events[n_chunks - 1], 0));
     }
+    stamp(s);
     SB_CUDA(cudaStreamSynchronize(s));
     SB_CUDA(cudaStreamSynchronize(c));
+    if (trace && n_tev > 1 && (rank == 0 || rank == world - 1)) {
+        fprintf(stderr, "[run_host_sharded rank %d] ms since call start: barrier0 done", rank);
+        for (int i = 1; i < n_tev; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            if (i == n_tev - 1) fprintf(stderr, " | passes + C out done %.3f", ms);
+            else if (i == 1) fprintf(stderr, " %.3f | chunks (pushed, landed everywhere):", ms);
+            else fprintf(stderr, " %.3f", ms);
+        }
+        fprintf(stderr, "\n");
+    }
+    for (int i = 0; i < n_tev; ++i) cudaEventDestroy(tev[i]);
     return 0;
 }
 
