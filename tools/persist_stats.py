@@ -1,4 +1,5 @@
-"""Persistent launch statistics (needs the stats build: SPMM_B200_LIB=hpc_b200/libspmm_b200_stats.so, -DSPMM_B200_PERSIST_STATS):
+"""Persistent launch statistics (needs the stats build: `make -C hpc_b200/csrc stats`, then
+SPMM_B200_LIB=$PWD/hpc_b200/libspmm_b200_stats.so python tools/persist_stats.py):
 polls of the row-group counters, blocked waits and their total clocks, per run, for one rank's block of an N-way partition."""
 import json, sys
 import numpy as np, torch
