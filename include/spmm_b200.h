@@ -82,8 +82,9 @@ int spmm_b200_set_option(spmm_b200_t h, const char *name, long long value);
  * Runs on `stream` and synchronises it before returning.
  * SNAPSHOT: for feat_in % 4 == 0 the plan stages a copy of idx/val ({col, val} panels) and run() reads only that
  * copy — unlike the reference's SpMMOpt::run, which reads idx/val at run time (PA4/workspace/src/spmm_opt.cu:22-25).
- * A caller that rewrites d_val (or d_idx without changing any row's length) in place afterwards must call
- * spmm_b200_refresh_values before the next run; a change of ptr needs a new preprocess. */
+ * A caller that rewrites d_val in place afterwards (or d_idx, if the plan has a single column block and no row changes
+ * its length) must call spmm_b200_refresh_values before the next run; any other change of the structure needs a new
+ * preprocess. */
 int spmm_b200_preprocess(spmm_b200_t h, const float *vin, float *vout, void *stream);
 
 /* Re-stages the plan's {col, val} panels from the caller's current d_idx / d_val (same ptr), asynchronously on
@@ -94,7 +95,10 @@ int spmm_b200_refresh_values(spmm_b200_t h, void *stream);
 /* SpMM::run(float *vin, float *vout)  (spmm_base.h:32; PA4/handout/src/spmm_ref.cu:27-30).
  * Asynchronous on `stream` (a cudaStream_t; NULL = the default stream, as in the reference).
  * Fully overwrites vout[num_v*feat_in]; does not depend on its previous contents. Runs of one handle must not
- * overlap in time (they share the handle's partial-row workspace): issue them on one stream, or synchronise. */
+ * overlap in time (they share the handle's partial-row workspace): issue them on one stream, or synchronise.
+ * With several column blocks half of the launches go out on a second stream owned by the handle, forked from and
+ * joined back to `stream` by events inside the call: to the caller everything is ordered on `stream` (also under
+ * CUDA-graph capture). */
 int spmm_b200_run(spmm_b200_t h, const float *vin, float *vout, void *stream);
 
 /* run, plus the device time of its kernel in milliseconds (CUDA events on `stream` around the
