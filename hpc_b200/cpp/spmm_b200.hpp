@@ -77,9 +77,23 @@ class SpMMB200 : public SpMM {
     // asynchronous on the stream (default stream unless set_stream), like SpMMRef::run (spmm_ref.cu:27-30)
     virtual void run(float *vin, float *vout) { check(spmm_b200_run(h_, vin, vout, stream_), "run"); }
 
+    // re-stage the plan's copy of idx / val after the caller changed the edge values in place (the reference's
+    // SpMMOpt::run reads them live, PA4/workspace/src/spmm_opt.cu:22-25)
+    void refresh_values() { check(spmm_b200_refresh_values(h_, stream_), "refresh_values"); }
+    // host buffers in and out: upload B band by band under the passes, final rows stored straight into pinned vout
+    void run_host(const float *h_vin, float *h_vout) { check(spmm_b200_run_host(h_, h_vin, h_vout, stream_), "run_host"); }
+    // the operator over A^T (gradient dB = A^T dC): run(dC, dB). Owns its CSR; delete it before this operator.
+    SpMMB200 *transposed(int feat = -1) const {
+        spmm_b200_t t = nullptr;
+        check(spmm_b200_create_transposed(h_, feat < 0 ? this->feat_in : feat, stream_, &t), "create_transposed");
+        return new SpMMB200(t, feat < 0 ? this->feat_in : feat, stream_);
+    }
+
     spmm_b200_t handle() const { return h_; }
 
    private:
+    // adopts a handle made by the library (the transposed operator); d_ptr / d_idx stay NULL: the handle owns its CSR
+    SpMMB200(spmm_b200_t adopted, int feat, cudaStream_t s) : SpMM(nullptr, nullptr, 0, 0, feat), h_(adopted), stream_(s) {}
     void create() { check(spmm_b200_create(d_ptr, d_idx, d_val, num_v, num_e, feat_in, &h_), "create"); }
     static void check(int rc, const char *what) {
         if (rc == 0) return;
