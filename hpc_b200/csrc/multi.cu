@@ -123,6 +123,16 @@ int spmm_b200_mg_create(const int *h_ptr, const int *h_idx, const float *h_val, 
     if (!out || !h_ptr || num_v < 0 || num_e < 0 || feat_in < 0 || n_devices < 1 || n_devices > kMaxGather ||
         (num_e > 0 && (!h_idx || !h_val)))
         return mg_fail("spmm_b200_mg_create: bad arguments");
+    // the partition below indexes idx / val by ptr: refuse an inconsistent ptr before anything is sliced
+    if (h_ptr[0] != 0 || h_ptr[num_v] != num_e) {
+        set_error("spmm_b200_mg_create: CSR ptr is inconsistent: ptr[0]=%d ptr[num_v]=%d num_e=%d", h_ptr[0], h_ptr[num_v], num_e);
+        return SPMM_B200_EINVAL;
+    }
+    for (int r = 0; r < num_v; ++r)
+        if (h_ptr[r + 1] < h_ptr[r]) {
+            set_error("spmm_b200_mg_create: CSR ptr decreases at row %d", r);
+            return SPMM_B200_EINVAL;
+        }
     int visible = 0;
     SB_CUDA(cudaGetDeviceCount(&visible));
     for (int g = 0; g < n_devices; ++g) {

@@ -55,6 +55,21 @@ def test_feat_zero_and_b_rows_without_gpu():
     assert lib.spmm_b200_destroy(h) == 0
 
 
+def test_mg_create_rejects_bad_csr_without_gpu():
+    """spmm_b200_mg_create validates the host CSR before it slices it (status code, no crash, no GPU needed for that)."""
+    from hpc_b200._lib import lib
+    h = ctypes.c_void_p()
+    ptr = (ctypes.c_int * 4)(0, 2, 1, 3)          # decreases at row 1
+    idx = (ctypes.c_int * 3)(0, 1, 2)
+    val = (ctypes.c_float * 3)(1, 2, 3)
+    assert lib.spmm_b200_mg_create(ptr, idx, val, 3, 3, 4, 1, None, ctypes.byref(h)) == -1
+    assert b"decreases" in lib.spmm_b200_last_error()
+    ptr2 = (ctypes.c_int * 4)(0, 1, 2, 2)         # ptr[num_v] != num_e
+    assert lib.spmm_b200_mg_create(ptr2, idx, val, 3, 3, 4, 1, None, ctypes.byref(h)) == -1
+    assert b"inconsistent" in lib.spmm_b200_last_error()
+    assert lib.spmm_b200_mg_create(ptr2, idx, val, 3, 2, 4, 99, None, ctypes.byref(h)) == -1     # too many devices
+
+
 def test_host_only_graph_library_matches():
     """libspmm_b200_graph.so (graph.cpp alone, what bench.py's CPU reference arm loads) has no CUDA dependency and
     generates the same graph as the main library."""
