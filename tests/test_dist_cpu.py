@@ -96,3 +96,21 @@ def test_row_partition_helpers():
         assert lp[0] == 0 and lp[-1] == e1 - e0
         tot += e1 - e0
     assert tot == ptr[-1]
+
+
+def test_row_partition_cost_balanced():
+    """RowPartition with the plan's per-row overhead (row_cost): the weighted rule of spmm_b200_partition_rows_weighted,
+    restated in oracle/plan_oracle.py; blocks still tile the rows and the slices line up."""
+    from oracle import plan_oracle as P
+    ptr, _ = H.gen_named_graph("arxiv")
+    for world, rc in ((4, 5), (8, 1)):
+        part = RowPartition(ptr, world, row_cost=rc)
+        assert np.array_equal(part.bounds, P.partition_rows(ptr, world, rc))
+        assert part.bounds[0] == 0 and part.bounds[-1] == len(ptr) - 1
+        tot = 0
+        for g in range(world):
+            e0, e1 = part.nnz_range(g)
+            lp = part.local_ptr(g)
+            assert lp[0] == 0 and lp[-1] == e1 - e0
+            tot += e1 - e0
+        assert tot == ptr[-1]
