@@ -36,7 +36,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
 
 // grid-stride float4 copy of this rank's slice into the peers' copies of B
 __global__ void __launch_bounds__(256) push_rows_kernel(const float4 *__restrict__ src, long long off4, long long n4, int n,
-                                                        PtrTable tg, int skip, float *mc) {
+                                                        const __grid_constant__ PtrTable tg, int skip, float *mc) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const float4 v = __ldcs(src + i);
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const float4 *__restrict
 
 // one thread per rank: publish my arrival everywhere, then wait for everybody's in my own flag array.
 // Epochs only grow (one per call and phase), compared wrap-safe.
-__global__ void xrank_barrier_kernel(FlagTable fl, int world, int rank, int phase, unsigned int epoch) {
+__global__ void xrank_barrier_kernel(const __grid_constant__ FlagTable fl, int world, int rank, int phase, unsigned int epoch) {
     const int t = threadIdx.x;
     if (t >= world) return;
     __threadfence_system();   // whatever this stream wrote before (peer pushes of the previous kernel) is visible first
