@@ -358,10 +358,18 @@ def build_sharded(ctx, H, shape, k, opts, graph=None):
     vin = torch.empty(m * k, dtype=torch.float32, device=ctx.dev)
     H.fill_normal(vin, SEED, 2)
     vout = torch.empty(max(1, sh.local_rows * k), dtype=torch.float32, device=ctx.dev)
+    torch.cuda.synchronize(ctx.dev)   # the input fills are queued kernels: keep them out of the preprocess clock
     t0 = time.perf_counter()
     sh.preprocess(vin, vout)
+    torch.cuda.synchronize(ctx.dev)
+    first_s = time.perf_counter() - t0
+    # the first plan build of a process also pays CUDA's lazy kernel loading and the first big cudaMalloc / pinned
+    # staging allocations; the same call again (the plan is rebuilt from scratch) is what every later operator costs
+    t0 = time.perf_counter()
+    sh.preprocess(vin, vout)
+    torch.cuda.synchronize(ctx.dev)
     prep_s = time.perf_counter() - t0
-    return ptr, idx, sh, vin, vout, prep_s
+    return ptr, idx, sh, vin, vout, (prep_s, first_s)
 
 
 def quick_measure(ctx, H, shape, k, steps=10, warmup=3, checksum=False, graph=None):
@@ -383,7 +391,8 @@ def quick_measure(ctx, H, shape, k, steps=10, warmup=3, checksum=False, graph=No
     ms, ms_warm = ctx.max_over_ranks([ts.mean(), tw.mean()])
     out = {"workload": f"{shape}_k{k}", "num_v": m, "nnz": nnz, "K": k, "n_gpus": ctx.world, "ms_per_step": round(ms, 5),
            "ms_per_step_l2_warm": round(ms_warm, 5), "gflops": round(2.0 * nnz * k / ms / 1e6, 1),
-           "launches_per_step": sh.op.launches_per_run, "preprocess_s": round(prep_s, 4),
+           "launches_per_step": sh.op.launches_per_run, "preprocess_s": round(prep_s[0], 4),
+           "preprocess_first_call_s": round(prep_s[1], 4),
            "l2": "flushed between iterations" if flush is not None else "inputs larger than L2"}
     if ctx.world == 1:
         peak, _ = measured_peaks()
@@ -586,7 +595,9 @@ def run_b200(args):
                 "partition": f"rows by nnz over {world} rank(s), B replicated, no collective",
                 "plan": {kk: info[kk] for kk in ("seg_len", "kslice", "n_slices", "lanes", "vec", "n_col_blocks", "n_light", "n_heavy", "n_seg",
                                                  "persistent", "n_row_groups", "n_tickets")},
-                "preprocess_s": round(prep_s, 4), "per_rank_ms": [round(x, 5) for x in per_rank_ms],
+                "preprocess_s": round(prep_s[0], 4), "preprocess_first_call_s": round(prep_s[1], 4),
+                "preprocess_note": "preprocess_s = the plan rebuilt by a second preprocess call; first call of the process adds lazy kernel loading and first allocations",
+                "per_rank_ms": [round(x, 5) for x in per_rank_ms],
                 "kernel_source_sha16": kernel_source_sha16(),
             },
             "sustained": {"ms_per_step": round(sus_ms, 5), "iters": n_sus, "seconds": round(sus_ms * n_sus / 1e3, 2),
