@@ -299,6 +299,8 @@ int spmm_b200_destroy(spmm_b200_t h) {
     return 0;
 }
 
+int spmm_b200_trim_memory(void) { return trim_plan_memory(); }
+
 int spmm_b200_launches_per_run(spmm_b200_t h) { return h ? h->plan.launches : 0; }
 
 int spmm_b200_plan_select(spmm_b200_t h, int col_block) {

@@ -122,6 +122,8 @@ struct BlockPlan {
 
 struct Plan {
     bool ready = false;
+    int device = -1;                // the device the plan's arrays live on (current device at preprocess)
+    cudaMemPool_t pool = nullptr;   // the library's retaining pool of that device, or null: plain cudaMalloc / cudaFree
     int seg_len = 0, kslice = 0, n_slices = 0, block = 128, lanes = 0, vec = 0, tune = 0, light_steps = 0;
     bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
     int n_col_blocks = 1;
@@ -191,6 +193,10 @@ float *host_out_mapping(const spmm_b200_handle *h, float *h_vout);
 // preprocess.cu
 int build_plan(spmm_b200_handle *h, cudaStream_t stream);
 void free_plan(Plan &p);
+// Plan arrays come from a library-owned CUDA memory pool per device that keeps freed blocks for the next plan
+// (preprocess.cu, "plan memory"); trim_plan_memory hands the unused ones of the current device back to the driver.
+cudaError_t plan_alloc(Plan &p, void **ptr, size_t bytes, cudaStream_t stream);
+int trim_plan_memory();
 int refresh_panels(spmm_b200_handle *h, cudaStream_t stream);
 
 // spmm_kernels.cu

@@ -216,6 +216,12 @@ class SpMMB200(SpMM):
             pass
 
 
+def trim_memory() -> None:
+    """Hand the plan memory pooled on the current device that no live operator uses back to the driver
+    (`spmm_b200_trim_memory`)."""
+    check(lib.spmm_b200_trim_memory())
+
+
 def fill_normal(t: torch.Tensor, seed: int, stream_id: int, mean: float = 0.0, stddev: float = 0.1) -> torch.Tensor:
     """Counter-based N(mean, stddev) fill (the engine's stand-in for curandGenerateNormal, data.h:31)."""
     if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():

@@ -121,8 +121,15 @@ int spmm_b200_set_gather(spmm_b200_t h, int n_targets, float *const *targets, fl
  * destroy it before h. spmm_b200_refresh_values on it re-reads h's current values. Synchronises `stream`. */
 int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *stream, spmm_b200_t *out);
 
-/* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). */
+/* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). Waits for the device to finish what still reads the plan.
+ * The plan's arrays go back to a memory pool the library keeps per device (cudaMemPool, release threshold = max), from
+ * which the next preprocess on that device takes them: creating, re-planning and destroying operators does not pay the
+ * driver's allocate / release cost again and again. SPMM_B200_POOL=0 in the environment selects plain cudaMalloc/cudaFree. */
 int spmm_b200_destroy(spmm_b200_t h);
+
+/* Hands the pooled memory that no live plan uses on the CURRENT device back to the driver (no reference counterpart;
+ * the reference's cudaFree in ~SpMMOpt does it per operator). Synchronises the device. */
+int spmm_b200_trim_memory(void);
 
 /* Host-buffer convenience for callers that hold B and C on the host: H2D(vin) → run → D2H(vout)
  * on `stream`, then synchronise. The handle keeps device staging buffers of num_v*feat_in floats. With column

@@ -309,6 +309,70 @@ def test_call_protocol_and_idempotence():
     op.close()
 
 
+def test_plan_memory_is_recycled_and_trimmed():
+    """Plan arrays come from the library's retaining memory pool (preprocess.cu, "plan memory"): re-planning on one handle,
+    on another stream, destroying and creating operators and trimming the pool in between never changes a bit."""
+    ptr, idx = H.gen_named_graph("c0")
+    K = 64
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    op = H.SpMMB200(g, K, col_blocks=3, seg_len=32)
+    op.preprocess(vin, vout)
+    op.run(vin, vout)
+    first = vout.clone()
+    s = torch.cuda.Stream()
+    for rep in range(3):
+        vout.fill_(float("nan"))
+        if rep == 1:
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):          # blocks freed in the legacy stream's order are taken over on another stream
+                op.preprocess(vin, vout)
+                op.run(vin, vout)
+            s.synchronize()
+        else:
+            op.preprocess(vin, vout)
+            op.run(vin, vout)
+        assert torch.equal(first, vout)
+    op.close()
+    H.trim_memory()
+    H.trim_memory()                             # nothing left to return: still fine
+    op = H.SpMMB200(g, K, col_blocks=3, seg_len=32)
+    op.preprocess(vin, vout)
+    other = H.SpMMB200(g, K)                    # two live plans next to each other
+    vout2 = torch.empty_like(vout)
+    other.preprocess(vin, vout2)
+    H.trim_memory()                             # live plans stay intact
+    vout.fill_(float("nan"))
+    op.run(vin, vout)
+    other.run(vin, vout2)
+    assert torch.equal(first, vout)
+    check_against_oracle(ptr, idx, K, other, g, vin, vout2.cpu().numpy().reshape(-1, K))
+    op.close()
+    other.close()
+
+
+def test_plain_cuda_malloc_path_without_the_pool():
+    """SPMM_B200_POOL=0: the same results with cudaMalloc / cudaFree (the pool is an allocator, nothing else)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch, numpy as np; sys.path.insert(0, '.'); import hpc_b200 as H\n"
+        "ptr, idx = H.gen_named_graph('c0'); M, nnz, K = len(ptr) - 1, len(idx), 64\n"
+        "g = H.CSR(M, nnz, torch.from_numpy(ptr).cuda(), torch.from_numpy(idx).cuda(), H.fill_normal(torch.empty(nnz, device='cuda'), 123, 1))\n"
+        "vin = H.fill_normal(torch.empty(M * K, device='cuda'), 123, 2); vout = torch.empty(M * K, device='cuda')\n"
+        "op = H.SpMMB200(g, K, col_blocks=3, seg_len=32)\n"
+        "for _ in range(2): op.preprocess(vin, vout); op.run(vin, vout)\n"
+        "H.trim_memory(); torch.cuda.synchronize()\n"
+        "print(int(vout.view(torch.int32).to(torch.int64).sum())); op.close()\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sums = []
+    for pool in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, "SPMM_B200_POOL": pool}, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        sums.append(int(r.stdout.strip().splitlines()[-1]))
+    assert sums[0] == sums[1]
+
+
 def test_preprocess_rejects_inconsistent_csr():
     """Bad inputs come back as status codes with a message (the reference asserts / exits: data.cu:40-45, util.h:63-84)."""
     ptr, idx = H.gen_named_graph("c0")
