@@ -89,6 +89,9 @@ class SpMMB200 : public SpMM {
         return new SpMMB200(t, feat < 0 ? this->feat_in : feat, stream_);
     }
 
+    // destroyed operators leave their plan memory in the library's pool for the next one; this hands it back to the driver
+    static void trim_memory() { check(spmm_b200_trim_memory(), "trim_memory"); }
+
     spmm_b200_t handle() const { return h_; }
 
    private:
