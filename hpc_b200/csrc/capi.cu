@@ -284,10 +284,16 @@ int spmm_b200_run_host(spmm_b200_t h, const float *h_vin, float *h_vout, void *s
 int spmm_b200_destroy(spmm_b200_t h) {
     if (!h) return 0;
     free_plan(h->plan);
-    cudaFree(h->t_ptr);
-    cudaFree(h->t_idx);
-    cudaFree(h->t_val);
-    cudaFree(h->t_perm);
+    if (h->t_ptr || h->t_idx || h->t_val || h->t_perm) {   // the transposed operator's CSR: back to its device's pool
+        int cur = -1;
+        const bool hop = h->t_device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != h->t_device && cudaSetDevice(h->t_device) == cudaSuccess;
+        cudaDeviceSynchronize();
+        pool_free(h->t_ptr, cudaStreamLegacy);
+        pool_free(h->t_idx, cudaStreamLegacy);
+        pool_free(h->t_val, cudaStreamLegacy);
+        pool_free(h->t_perm, cudaStreamLegacy);
+        if (hop) cudaSetDevice(cur);
+    }
     cudaFree(h->d_stage_in);
     cudaFree(h->d_stage_out);
     for (cudaEvent_t e : h->band_events) cudaEventDestroy(e);
@@ -299,7 +305,7 @@ int spmm_b200_destroy(spmm_b200_t h) {
     return 0;
 }
 
-int spmm_b200_trim_memory(void) { return trim_plan_memory(); }
+int spmm_b200_trim_memory(void) { return trim_pool_memory(); }
 
 int spmm_b200_launches_per_run(spmm_b200_t h) { return h ? h->plan.launches : 0; }
 

@@ -122,8 +122,7 @@ struct BlockPlan {
 
 struct Plan {
     bool ready = false;
-    int device = -1;                // the device the plan's arrays live on (current device at preprocess)
-    cudaMemPool_t pool = nullptr;   // the library's retaining pool of that device, or null: plain cudaMalloc / cudaFree
+    int device = -1;   // the device the plan's arrays live on (the current device at preprocess)
     int seg_len = 0, kslice = 0, n_slices = 0, block = 128, lanes = 0, vec = 0, tune = 0, light_steps = 0;
     bool scalar = false;   // K % 4 != 0: scalar fallback kernel, no segments
     int n_col_blocks = 1;
@@ -181,6 +180,7 @@ struct spmm_b200_handle {
     long long rep_h2d_bytes = 0;   // host-to-device bytes of the last run_host_sharded call
     // transposed operator (transpose.cu): the CSR of A^T is owned by this handle; t_src is the handle it was built from
     int *t_ptr = nullptr, *t_idx = nullptr, *t_perm = nullptr;
+    int t_device = -1;   // the device whose pool (pool.cu) these arrays came from
     float *t_val = nullptr;
     const spmm_b200_handle *t_src = nullptr;
 };
@@ -193,10 +193,11 @@ float *host_out_mapping(const spmm_b200_handle *h, float *h_vout);
 // preprocess.cu
 int build_plan(spmm_b200_handle *h, cudaStream_t stream);
 void free_plan(Plan &p);
-// Plan arrays come from a library-owned CUDA memory pool per device that keeps freed blocks for the next plan
-// (preprocess.cu, "plan memory"); trim_plan_memory hands the unused ones of the current device back to the driver.
-cudaError_t plan_alloc(Plan &p, void **ptr, size_t bytes, cudaStream_t stream);
-int trim_plan_memory();
+// pool.cu: plan arrays (and the transposed operator's CSR) come from a library-owned CUDA memory pool per device that
+// keeps freed blocks for the next plan; all three act on the CURRENT device.
+cudaError_t pool_alloc(void **ptr, size_t bytes, cudaStream_t stream);
+void pool_free(void *ptr, cudaStream_t stream);
+int trim_pool_memory();
 int refresh_panels(spmm_b200_handle *h, cudaStream_t stream);
 
 // spmm_kernels.cu

@@ -24,7 +24,6 @@
 
 #include <algorithm>
 #include <chrono>
-#include <mutex>
 #include <vector>
 
 #include "common.h"
@@ -43,71 +42,13 @@ struct PrepTrace {
     }
 };
 
-// ---- plan memory -------------------------------------------------------------------------------------------------
-// Handing a reddit-sized plan (about 1 GB of panels) back to the driver with cudaFree took 0.4-0.7 s inside a
-// process that also runs torch on the B200 boxes (profiles/r02_notes.md section 10) — per destroyed operator, and per
-// preprocess call on a handle that already had a plan. Plan arrays therefore come from a CUDA memory pool per device
-// that the library owns and that keeps freed blocks (release threshold = max): the next plan takes them over in
-// microseconds. spmm_b200_trim_memory() returns what no live plan uses; SPMM_B200_POOL=0 selects cudaMalloc/cudaFree.
-namespace {
-constexpr int kMaxPoolDevices = 64;
-std::mutex g_pool_mu;
-cudaMemPool_t g_pool[kMaxPoolDevices];
-int g_pool_state[kMaxPoolDevices];   // 0 not tried yet, 1 ready, -1 unavailable (old driver, SPMM_B200_POOL=0)
-
-cudaMemPool_t device_pool(int dev) {
-    if (dev < 0 || dev >= kMaxPoolDevices) return nullptr;
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (g_pool_state[dev] == 0) {
-        g_pool_state[dev] = -1;
-        const char *env = getenv("SPMM_B200_POOL");
-        int supported = 0;
-        if (!(env && env[0] == '0') && cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess &&
-            supported) {
-            cudaMemPoolProps props = {};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = dev;
-            unsigned long long keep = ~0ull;
-            if (cudaMemPoolCreate(&g_pool[dev], &props) == cudaSuccess) {
-                if (cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess)
-                    g_pool_state[dev] = 1;
-                else
-                    cudaMemPoolDestroy(g_pool[dev]);
-            }
-        }
-        cudaGetLastError();   // an unavailable pool is not an error of the call that asked
-    }
-    return g_pool_state[dev] == 1 ? g_pool[dev] : nullptr;
-}
-}   // namespace
-
-cudaError_t plan_alloc(Plan &p, void **ptr, size_t bytes, cudaStream_t stream) {
-    if (p.pool) return cudaMallocFromPoolAsync(ptr, bytes, p.pool, stream);
-    return cudaMalloc(ptr, bytes);
-}
-
-int trim_plan_memory() {
-    int dev = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= kMaxPoolDevices) return 0;
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (g_pool_state[dev] != 1) return 0;
-    SB_CUDA(cudaDeviceSynchronize());   // blocks freed in stream order become releasable once their stream got there
-    SB_CUDA(cudaMemPoolTrimTo(g_pool[dev], 0));
-    return 0;
-}
-
 void free_plan(Plan &p) {
+    // the arrays came from the library's pool of p.device (pool.cu): wait, like cudaFree would, for whatever still reads the
+    // plan, then hand them back in the order of the legacy stream
     int cur = -1;
     const bool hop = p.device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != p.device && cudaSetDevice(p.device) == cudaSuccess;
-    // like cudaFree, wait for whatever still reads the plan; pool blocks then go back in the order of the legacy stream
-    if (p.pool && (p.d_split || !p.blocks.empty())) cudaDeviceSynchronize();
-    auto release = [&](void *q) {
-        if (!q) return;
-        if (p.pool) cudaFreeAsync(q, cudaStreamLegacy);
-        else cudaFree(q);
-    };
+    if (p.d_split || !p.blocks.empty()) cudaDeviceSynchronize();
+    auto release = [](void *q) { pool_free(q, cudaStreamLegacy); };
     for (BlockPlan &b : p.blocks) {
         release(b.d_row_perm);
         release(b.d_light_desc);
@@ -564,9 +505,9 @@ static void plan_block_host(const spmm_b200_handle *h, const int *rb, const int 
 }
 
 template <class T>
-static int upload_vec(Plan &p, T **dst, const std::vector<T> &v, cudaStream_t stream) {
+static int upload_vec(T **dst, const std::vector<T> &v, cudaStream_t stream) {
     if (v.empty()) return 0;
-    SB_CUDA(plan_alloc(p, (void **)dst, sizeof(T) * v.size(), stream));
+    SB_CUDA(pool_alloc((void **)dst, sizeof(T) * v.size(), stream));
     SB_CUDA(cudaMemcpyAsync(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, stream));
     return 0;
 }
@@ -588,8 +529,7 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         p.ready = true;
         return 0;
     }
-    SB_CUDA(cudaGetDevice(&p.device));
-    p.pool = device_pool(p.device);
+    SB_CUDA(cudaGetDevice(&p.device));   // the plan's arrays come from this device's pool (pool.cu)
     p.block = (int)h->opt_block;
     p.scalar = (K % 4) != 0;
     p.kslice = h->opt_kslice > 0 ? (int)h->opt_kslice : auto_kslice(M, K);
@@ -662,8 +602,8 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         band_begin.push_back(b_rows);
     }
     if (nb > 1) {
-        if (plan_alloc(p, (void **)&p.d_split, sizeof(int) * (size_t)(nb + 1) * M, stream) != cudaSuccess)
-            return with_flags(cuda_fail(cudaGetLastError(), "plan_alloc(split)", __FILE__, __LINE__));
+        if (pool_alloc((void **)&p.d_split, sizeof(int) * (size_t)(nb + 1) * M, stream) != cudaSuccess)
+            return with_flags(cuda_fail(cudaGetLastError(), "pool_alloc(split)", __FILE__, __LINE__));
         rc = launch_split_rows(h->d_ptr, h->d_idx, M, nb, band_begin.data(), p.d_split, d_flags + 1, stream);
         if (rc) return with_flags(rc);
         split.resize((size_t)(nb + 1) * M);
@@ -681,8 +621,7 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         return SPMM_B200_EINVAL;
     }
     if (nb > 1 && flags[1]) {
-        if (p.pool) cudaFreeAsync(p.d_split, stream);
-        else cudaFree(p.d_split);
+        pool_free(p.d_split, stream);
         p.d_split = nullptr;
         split.clear();
         nb = 1;
@@ -758,16 +697,16 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         return SPMM_B200_EINVAL;
     }
     if (lp_total) {
-        SB_CUDA(plan_alloc(p, (void **)&p.d_lpanel_all, sizeof(int2) * (size_t)lp_total, stream));
+        SB_CUDA(pool_alloc((void **)&p.d_lpanel_all, sizeof(int2) * (size_t)lp_total, stream));
         SB_CUDA(cudaMemsetAsync(p.d_lpanel_all, 0xFF, sizeof(int2) * (size_t)lp_total, stream));   // nop entries
     }
-    if (pn_total) SB_CUDA(plan_alloc(p, (void **)&p.d_panel_all, sizeof(int2) * (size_t)pn_total, stream));
-    if (seg_total) SB_CUDA(plan_alloc(p, (void **)&p.d_part_all, sizeof(float) * (size_t)seg_total * K, stream));
+    if (pn_total) SB_CUDA(pool_alloc((void **)&p.d_panel_all, sizeof(int2) * (size_t)pn_total, stream));
+    if (seg_total) SB_CUDA(pool_alloc((void **)&p.d_part_all, sizeof(float) * (size_t)seg_total * K, stream));
     if (heavy_total) {
         // n_heavy + 1 slots per band, so that a band's counters sit at its absolute heavy-row base (the persistent
         // launch addresses them that way, like heavy_seg0)
         const size_t slots = (size_t)(heavy_total + nb) * p.n_slices;
-        SB_CUDA(plan_alloc(p, (void **)&p.d_seg_count_all, sizeof(int) * slots, stream));
+        SB_CUDA(pool_alloc((void **)&p.d_seg_count_all, sizeof(int) * slots, stream));
         SB_CUDA(cudaMemsetAsync(p.d_seg_count_all, 0, sizeof(int) * slots, stream));
     }
     tr.lap("arena allocation");
@@ -792,19 +731,19 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
         bp.task_group = x.task_group;
         // first task of the second half of the row groups (tasks are in row order, so the groups are contiguous)
         bp.split_task = (int)(std::lower_bound(x.task_group.begin(), x.task_group.end(), (p.n_groups + 1) / 2) - x.task_group.begin());
-        if ((rc = upload_vec(p, &bp.d_row_perm, x.row_perm, stream))) return rc;
-        if ((rc = upload_vec(p, &bp.d_light_desc, x.light, stream))) return rc;
-        if ((rc = upload_vec(p, &bp.d_utask, x.utask, stream))) return rc;
-        if ((rc = upload_vec(p, &bp.d_ltask, x.ltasks, stream))) return rc;
+        if ((rc = upload_vec(&bp.d_row_perm, x.row_perm, stream))) return rc;
+        if ((rc = upload_vec(&bp.d_light_desc, x.light, stream))) return rc;
+        if ((rc = upload_vec(&bp.d_utask, x.utask, stream))) return rc;
+        if ((rc = upload_vec(&bp.d_ltask, x.ltasks, stream))) return rc;
         if (bp.n_ltask > 0) {
             bp.d_lpanel = p.d_lpanel_all + lp_off;
             if ((rc = launch_build_lpanel(bp.d_light_desc, bp.n_light, groups, K / 4, h->d_idx, h->d_val, bp.d_lpanel, stream))) return rc;
         }
         if (bp.n_heavy > 0) {
-            if ((rc = upload_vec(p, &bp.d_seg_hrow, x.seg_hrow, stream))) return rc;
-            if ((rc = upload_vec(p, &bp.d_heavy_rows, x.heavy_rows, stream))) return rc;
-            if ((rc = upload_vec(p, &bp.d_heavy_seg0, x.heavy_seg0, stream))) return rc;
-            if ((rc = upload_vec(p, &bp.d_seg_desc, x.segs, stream))) return rc;
+            if ((rc = upload_vec(&bp.d_seg_hrow, x.seg_hrow, stream))) return rc;
+            if ((rc = upload_vec(&bp.d_heavy_rows, x.heavy_rows, stream))) return rc;
+            if ((rc = upload_vec(&bp.d_heavy_seg0, x.heavy_seg0, stream))) return rc;
+            if ((rc = upload_vec(&bp.d_seg_desc, x.segs, stream))) return rc;
             bp.d_seg_count = p.d_seg_count_all + (heavy_off + b) * p.n_slices;
             bp.d_panel = p.d_panel_all + pn_off;
             bp.d_part = p.d_part_all + seg_off * K;
@@ -864,12 +803,12 @@ int build_plan(spmm_b200_handle *h, cudaStream_t stream) {
             seg0 += (long long)x.segs.size();
         }
         p.n_ptask = (int)ptask.size();
-        if ((rc = upload_vec(p, &p.d_ptask, ptask, stream))) return rc;
-        if ((rc = upload_vec(p, &p.d_pseg_desc, pseg, stream))) return rc;
-        if ((rc = upload_vec(p, &p.d_pseg_hrow, pseg_hrow, stream))) return rc;
-        if ((rc = upload_vec(p, &p.d_pheavy_seg0, pheavy_seg0, stream))) return rc;
+        if ((rc = upload_vec(&p.d_ptask, ptask, stream))) return rc;
+        if ((rc = upload_vec(&p.d_pseg_desc, pseg, stream))) return rc;
+        if ((rc = upload_vec(&p.d_pseg_hrow, pseg_hrow, stream))) return rc;
+        if ((rc = upload_vec(&p.d_pheavy_seg0, pheavy_seg0, stream))) return rc;
         // ticket, exited warps, per-group completions, watchdog: one 128-byte line each
-        SB_CUDA(plan_alloc(p, (void **)&p.d_ctr, sizeof(unsigned int) * ctr_words(p.n_groups), stream));
+        SB_CUDA(pool_alloc((void **)&p.d_ctr, sizeof(unsigned int) * ctr_words(p.n_groups), stream));
         SB_CUDA(cudaMemsetAsync(p.d_ctr, 0, sizeof(unsigned int) * ctr_words(p.n_groups), stream));
         p.persist_grid = persistent_grid(p.lanes, p.vec, p.tune, p.block);
         // Tickets per draw. A batch delays the completion of its last task by the tasks before it, and the next band's

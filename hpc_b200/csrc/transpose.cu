@@ -87,12 +87,18 @@ extern "C" int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *str
     }
     int *row_of = nullptr, *pos = nullptr, *keys_out = nullptr, *bad = nullptr;
     void *tmp = nullptr;
+    // scratch and the new CSR come from the library's pool (pool.cu), stream-ordered on `s`
+    auto drop_scratch = [&]() {
+        pool_free(row_of, s);
+        pool_free(pos, s);
+        pool_free(keys_out, s);
+        pool_free(tmp, s);
+        pool_free(bad, s);
+    };
     auto fail = [&](int rc) {
-        cudaFree(row_of);
-        cudaFree(pos);
-        cudaFree(keys_out);
-        cudaFree(tmp);
-        cudaFree(bad);
+        cudaStreamSynchronize(s);   // whatever was queued may still read the scratch
+        cudaGetLastError();
+        drop_scratch();
         spmm_b200_destroy(t);
         return rc;
     };
@@ -101,15 +107,16 @@ extern "C" int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *str
         cudaError_t e__ = (call);                                                        \
         if (e__ != cudaSuccess) return fail(cuda_fail(e__, #call, __FILE__, __LINE__)); \
     } while (0)
-    TR_CUDA(cudaMalloc((void **)&t->t_ptr, sizeof(int) * ((size_t)rows_t + 1)));
-    TR_CUDA(cudaMalloc((void **)&t->t_idx, sizeof(int) * (size_t)std::max<long long>(1, nnz)));
-    TR_CUDA(cudaMalloc((void **)&t->t_val, sizeof(float) * (size_t)std::max<long long>(1, nnz)));
-    TR_CUDA(cudaMalloc((void **)&t->t_perm, sizeof(int) * (size_t)std::max<long long>(1, nnz)));
+    TR_CUDA(cudaGetDevice(&t->t_device));
+    TR_CUDA(pool_alloc((void **)&t->t_ptr, sizeof(int) * ((size_t)rows_t + 1), s));
+    TR_CUDA(pool_alloc((void **)&t->t_idx, sizeof(int) * (size_t)std::max<long long>(1, nnz), s));
+    TR_CUDA(pool_alloc((void **)&t->t_val, sizeof(float) * (size_t)std::max<long long>(1, nnz), s));
+    TR_CUDA(pool_alloc((void **)&t->t_perm, sizeof(int) * (size_t)std::max<long long>(1, nnz), s));
     TR_CUDA(cudaMemsetAsync(t->t_ptr, 0, sizeof(int) * ((size_t)rows_t + 1), s));
     if (nnz > 0) {
         // a column outside [0, rows_t) would corrupt the histogram: same check as preprocess
         int h_bad = 0;
-        TR_CUDA(cudaMalloc((void **)&bad, sizeof(int)));
+        TR_CUDA(pool_alloc((void **)&bad, sizeof(int), s));
         TR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
         int rc = launch_check_cols(h->d_idx, nnz, rows_t, bad, s);
         if (rc) return fail(rc);
@@ -119,9 +126,9 @@ extern "C" int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *str
             set_error("CSR idx holds a column outside [0, %d)", rows_t);
             return fail(SPMM_B200_EINVAL);
         }
-        TR_CUDA(cudaMalloc((void **)&row_of, sizeof(int) * (size_t)nnz));
-        TR_CUDA(cudaMalloc((void **)&pos, sizeof(int) * (size_t)nnz));
-        TR_CUDA(cudaMalloc((void **)&keys_out, sizeof(int) * (size_t)nnz));
+        TR_CUDA(pool_alloc((void **)&row_of, sizeof(int) * (size_t)nnz, s));
+        TR_CUDA(pool_alloc((void **)&pos, sizeof(int) * (size_t)nnz, s));
+        TR_CUDA(pool_alloc((void **)&keys_out, sizeof(int) * (size_t)nnz, s));
         // ptr of A^T: counts shifted by one, then an inclusive scan in place == exclusive scan of the counts
         col_histogram_kernel<<<grid_for(nnz), 256, 0, s>>>(h->d_idx, nnz, t->t_ptr + 1);
         TR_CUDA(cudaGetLastError());
@@ -130,7 +137,7 @@ extern "C" int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *str
         int bits = 1;
         while (bits < 31 && (1ll << bits) < (long long)rows_t) ++bits;
         TR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h->d_idx, keys_out, pos, t->t_perm, (int)nnz, 0, bits, s));
-        TR_CUDA(cudaMalloc(&tmp, std::max(scan_bytes, sort_bytes)));
+        TR_CUDA(pool_alloc(&tmp, std::max(scan_bytes, sort_bytes), s));
         TR_CUDA(cub::DeviceScan::InclusiveSum(tmp, scan_bytes, t->t_ptr + 1, t->t_ptr + 1, rows_t, s));
         const long long threads = (long long)h->num_v * 32;
         if (h->num_v > 0) expand_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(h->d_ptr, h->num_v, row_of, pos);
@@ -142,11 +149,7 @@ extern "C" int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *str
     }
     TR_CUDA(cudaStreamSynchronize(s));
 #undef TR_CUDA
-    cudaFree(row_of);
-    cudaFree(pos);
-    cudaFree(keys_out);
-    cudaFree(tmp);
-    cudaFree(bad);
+    drop_scratch();
     t->d_ptr = t->t_ptr;
     t->d_idx = t->t_idx;
     t->d_val = t->t_val;

@@ -310,7 +310,7 @@ def test_call_protocol_and_idempotence():
 
 
 def test_plan_memory_is_recycled_and_trimmed():
-    """Plan arrays come from the library's retaining memory pool (preprocess.cu, "plan memory"): re-planning on one handle,
+    """Plan arrays come from the library's retaining memory pool (pool.cu): re-planning on one handle,
     on another stream, destroying and creating operators and trimming the pool in between never changes a bit."""
     ptr, idx = H.gen_named_graph("c0")
     K = 64
