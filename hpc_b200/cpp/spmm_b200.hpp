@@ -89,6 +89,13 @@ class SpMMB200 : public SpMM {
         return new SpMMB200(t, feat < 0 ? this->feat_in : feat, stream_);
     }
 
+    // the same matrix with every row in ascending column order — for CSR inputs whose rows are not column-sorted (they
+    // otherwise stay in one column block). Results associate in column order. Delete it before this operator.
+    SpMMB200 *column_sorted(int feat = -1) const {
+        spmm_b200_t t = nullptr;
+        check(spmm_b200_create_column_sorted(h_, feat < 0 ? this->feat_in : feat, stream_, &t), "create_column_sorted");
+        return new SpMMB200(t, feat < 0 ? this->feat_in : feat, stream_);
+    }
     // destroyed operators leave their plan memory in the library's pool for the next one; this hands it back to the driver
     static void trim_memory() { check(spmm_b200_trim_memory(), "trim_memory"); }
 

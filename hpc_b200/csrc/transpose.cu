@@ -37,6 +37,17 @@ __global__ void __launch_bounds__(256) expand_rows_kernel(const int *ptr, int nu
     }
 }
 
+// one warp per row of A: (row, column) as one 64-bit sort key per nonzero, and the identity permutation
+__global__ void __launch_bounds__(256) row_col_keys_kernel(const int *ptr, const int *idx, int num_v, unsigned long long *key, int *pos) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= num_v) return;
+    for (int i = ptr[gw] + lane; i < ptr[gw + 1]; i += 32) {
+        key[i] = ((unsigned long long)gw << 32) | (unsigned int)idx[i];
+        pos[i] = i;
+    }
+}
+
 __global__ void __launch_bounds__(256) gather_t_kernel(const int *perm, const int *row_of, const float *val, long long nnz, int *idx_t,
                                                        float *val_t) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -157,6 +168,83 @@ extern "C" int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *str
     t->num_e = (int)nnz;
     t->feat = feat_in;
     t->b_rows = h->num_v;   // A^T gathers rows of dC, which has as many rows as A
+    t->t_src = h;
+    *out = t;
+    return 0;
+}
+
+// The column-sorted operator: a second handle over the SAME matrix whose rows are stored in ascending column order
+// (equal columns keep their storage order: the radix sort is stable). For CSR inputs whose rows are not column-sorted —
+// which the plan otherwise keeps in one column block, because splitting an unsorted row at band boundaries would reorder
+// its FMA chain (preprocess.cu) — this is the opt-in that gives them the L2-resident bands: outputs then associate in
+// column order, i.e. they equal the reference run on the sorted CSR bit for bit and the reference run on the original
+// order within the split-row tolerance. Shares ptr with `h` (borrowed), owns idx / val / perm (pool.cu).
+extern "C" int spmm_b200_create_column_sorted(spmm_b200_t h, int feat_in, void *stream, spmm_b200_t *out) {
+    if (!h || !out || feat_in < 0) {
+        set_error("spmm_b200_create_column_sorted: bad arguments");
+        return SPMM_B200_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long nnz = h->num_e;
+    spmm_b200_handle *t = new (std::nothrow) spmm_b200_handle();
+    if (!t) {
+        set_error("spmm_b200_create_column_sorted: out of host memory");
+        return SPMM_B200_ENOMEM;
+    }
+    unsigned long long *key_in = nullptr, *key_out = nullptr;
+    int *pos = nullptr;
+    void *tmp = nullptr;
+    auto drop_scratch = [&]() {
+        pool_free(key_in, s);
+        pool_free(key_out, s);
+        pool_free(pos, s);
+        pool_free(tmp, s);
+    };
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(s);
+        cudaGetLastError();
+        drop_scratch();
+        spmm_b200_destroy(t);
+        return rc;
+    };
+#define TR_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) return fail(cuda_fail(e__, #call, __FILE__, __LINE__)); \
+    } while (0)
+    TR_CUDA(cudaGetDevice(&t->t_device));
+    const size_t cnt = (size_t)std::max<long long>(1, nnz);
+    TR_CUDA(pool_alloc((void **)&t->t_idx, sizeof(int) * cnt, s));
+    TR_CUDA(pool_alloc((void **)&t->t_val, sizeof(float) * cnt, s));
+    TR_CUDA(pool_alloc((void **)&t->t_perm, sizeof(int) * cnt, s));
+    if (nnz > 0) {
+        TR_CUDA(pool_alloc((void **)&key_in, sizeof(unsigned long long) * cnt, s));
+        TR_CUDA(pool_alloc((void **)&key_out, sizeof(unsigned long long) * cnt, s));
+        TR_CUDA(pool_alloc((void **)&pos, sizeof(int) * cnt, s));
+        const long long threads = (long long)h->num_v * 32;
+        row_col_keys_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(h->d_ptr, h->d_idx, h->num_v, key_in, pos);
+        TR_CUDA(cudaGetLastError());
+        int row_bits = 1;
+        while (row_bits < 31 && (1ll << row_bits) < (long long)h->num_v) ++row_bits;
+        size_t sort_bytes = 0;
+        TR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, key_in, key_out, pos, t->t_perm, (int)nnz, 0, 32 + row_bits, s));
+        TR_CUDA(pool_alloc(&tmp, sort_bytes, s));
+        // stable: nonzeros of one row with the same column keep their storage order
+        TR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sort_bytes, key_in, key_out, pos, t->t_perm, (int)nnz, 0, 32 + row_bits, s));
+        // idx_sorted[k] = idx[perm[k]], val_sorted[k] = val[perm[k]]
+        gather_t_kernel<<<grid_for(nnz), 256, 0, s>>>(t->t_perm, h->d_idx, h->d_val, nnz, t->t_idx, t->t_val);
+        TR_CUDA(cudaGetLastError());
+    }
+    TR_CUDA(cudaStreamSynchronize(s));
+#undef TR_CUDA
+    drop_scratch();
+    t->d_ptr = h->d_ptr;   // same rows, same lengths
+    t->d_idx = t->t_idx;
+    t->d_val = t->t_val;
+    t->num_v = h->num_v;
+    t->num_e = (int)nnz;
+    t->feat = feat_in;
+    t->b_rows = h->b_rows;
     t->t_src = h;
     *out = t;
     return 0;

@@ -119,6 +119,22 @@ class SpMMB200(SpMM):
             t.set_option(k, v)
         return t
 
+    def column_sorted(self, feat_in: int | None = None, **options) -> "SpMMB200":
+        """The operator over the same matrix with every row in ascending column order (spmm_b200_create_column_sorted): for
+        CSR inputs whose rows are not column-sorted, which otherwise stay in one column block. Results associate in column
+        order. The new operator borrows ptr, owns idx / val; close it before this one."""
+        t = object.__new__(SpMMB200)
+        t.g = None
+        t.num_e, t.num_v, t.b_rows = self.num_e, self.num_v, self.b_rows
+        t.feat_in = self.feat_in if feat_in is None else int(feat_in)
+        h = C.c_void_p()
+        check(lib.spmm_b200_create_column_sorted(self._h, t.feat_in, _stream(), C.byref(h)))
+        t._h = h
+        t._parent = self   # the C side copies b_rows from the source handle
+        for k, v in options.items():
+            t.set_option(k, v)
+        return t
+
     def refresh_values(self) -> None:
         """Re-stage the plan's copy of idx/val after the caller changed them in place (same ptr)."""
         check(lib.spmm_b200_refresh_values(self._h, _stream()))

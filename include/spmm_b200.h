@@ -121,6 +121,15 @@ int spmm_b200_set_gather(spmm_b200_t h, int n_targets, float *const *targets, fl
  * destroy it before h. spmm_b200_refresh_values on it re-reads h's current values. Synchronises `stream`. */
 int spmm_b200_create_transposed(spmm_b200_t h, int feat_in, void *stream, spmm_b200_t *out);
 
+/* The column-sorted operator (no reference counterpart): a new handle over the SAME matrix with every row stored in
+ * ascending column order (stable: equal columns keep their storage order), built on the device. A CSR whose rows are
+ * not column-sorted is otherwise kept in ONE column block — splitting an unsorted row at band boundaries would reorder
+ * its FMA chain — and loses the L2-resident bands on large graphs; this is the opt-in: outputs equal the reference
+ * run on the sorted CSR bit for bit (whole rows), and the reference run on the original order within the split-row
+ * tolerance 1e-5 * sum|terms|. Borrows h's ptr, owns idx / val; use it like any handle, destroy it before h.
+ * spmm_b200_refresh_values on it re-reads h's current values. Synchronises `stream`. */
+int spmm_b200_create_column_sorted(spmm_b200_t h, int feat_in, void *stream, spmm_b200_t *out);
+
 /* SpMMOpt::~SpMMOpt (PA4/workspace/include/spmm_opt.h:18-20). Waits for the device to finish what still reads the plan.
  * The plan's arrays go back to a memory pool the library keeps per device (cudaMemPool, release threshold = max), from
  * which the next preprocess on that device takes them: creating, re-planning and destroying operators does not pay the

@@ -122,7 +122,7 @@ def test_cpp_adapter_compiles_standalone_and_against_the_handout(tmp_path):
                   'SpMM *make(CSR *g, int k, const float *hb, float *hc) {\n'
                   '    SpMMB200 *a = new SpMMB200(g, k);\n'
                   '    a->set_option("seg_len", 256); a->refresh_values(); a->run_host(hb, hc); SpMMB200::trim_memory();\n'
-                  '    SpMMB200 *t = a->transposed(); delete t;\n'
+                  '    SpMMB200 *t = a->transposed(); delete t; t = a->column_sorted(); delete t;\n'
                   '    return a;\n}\n')
     base = ["nvcc", "-std=c++14", "-w", "-c", "-o", str(tmp_path / "t.o"), "-I", os.path.join(ROOT, "include"),
             "-I", os.path.join(ROOT, "hpc_b200", "cpp")]

@@ -9,6 +9,7 @@ output must pass the reference's own criterion (valid.cu:8 + test_spmm.cu:43).
 """
 import json
 import os
+from types import SimpleNamespace
 
 import numpy as np
 import pytest
@@ -551,6 +552,60 @@ def test_unsorted_columns_fall_back_to_one_block():
     assert op.plan_info()["n_col_blocks"] == 1
     assert np.array_equal(got.view(np.int32), O.spmm_literal(ptr, idx, val, b, 8).view(np.int32))
     op.close()
+
+
+def _shuffled_rows(ptr, idx, seed):
+    """The same graph with every row's columns in random storage order, and a duplicate column in the longest row."""
+    rng = np.random.default_rng(seed)
+    idx = idx.copy()
+    for r in range(len(ptr) - 1):
+        a, b = int(ptr[r]), int(ptr[r + 1])
+        idx[a:b] = rng.permutation(idx[a:b])
+    r = int(np.argmax(np.diff(ptr)))
+    idx[ptr[r]] = idx[ptr[r + 1] - 1]            # the same column twice: stability of the sort is observable
+    return idx
+
+
+@pytest.mark.parametrize("shape,K,opts", [("c0", 64, {"col_blocks": 3, "seg_len": 32}), ("arxiv", 256, {"col_blocks": 4}), ("c0", 33, {})])
+def test_column_sorted_operator(shape, K, opts):
+    """Rows that are not column-sorted keep ONE column block (bit-exact in storage order); the column-sorted operator
+    (spmm_b200_create_column_sorted) gets the bands and equals the oracle run on the stably sorted CSR bit for bit, and the
+    oracle run on the original order within the split-row tolerance."""
+    ptr, idx0 = H.gen_named_graph(shape)
+    idx = _shuffled_rows(ptr, idx0, 7)
+    g, vin, vout = dev_inputs(ptr, idx, K)
+    M = g.num_v
+    src = H.SpMMB200(g, K, **opts)
+    src.preprocess(vin, vout)
+    assert src.plan_info()["n_col_blocks"] == 1
+    op = src.column_sorted(**opts)
+    out = torch.full((M * K,), float("nan"), device=DEV)
+    op.preprocess(vin, out)
+    if "col_blocks" in opts:
+        assert op.plan_info()["n_col_blocks"] == opts["col_blocks"]
+    op.run(vin, out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(M, K)
+    val = g.val.cpu().numpy()
+    # the stable sort, restated: order inside a row by (column, storage position)
+    row_of = np.repeat(np.arange(M), np.diff(ptr))
+    perm = np.lexsort((np.arange(len(idx)), idx, row_of))
+    assert np.array_equal(row_of[perm], row_of)
+    check_against_oracle(ptr, idx[perm], K, op, SimpleNamespace(num_v=M, val=torch.from_numpy(val[perm])), vin, got)
+    ref0 = O.spmm_f32(ptr, idx, val, vin.cpu().numpy(), K)
+    ab = O.spmm_abssum(ptr, idx, val, vin.cpu().numpy(), K)
+    assert np.all(np.abs(got.astype(np.float64) - ref0) <= TOL * ab + 1e-30)
+    # re-weighted edges reach the sorted copy through refresh_values
+    g.val.mul_(-2.0)
+    op.refresh_values()
+    op.run(vin, out)
+    torch.cuda.synchronize()
+    heavy = op.heavy_row_set()
+    whole = np.asarray([r for r in range(M) if r not in heavy], np.int64)
+    want = O.spmm_f32(ptr, idx[perm], val[perm] * np.float32(-2.0), vin.cpu().numpy(), K)
+    assert np.array_equal(out.cpu().numpy().reshape(M, K)[whole].view(np.int32), want[whole].view(np.int32))
+    op.close()
+    src.close()
 
 
 def test_auto_row_order_rule():
