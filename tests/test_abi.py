@@ -55,6 +55,23 @@ def test_feat_zero_and_b_rows_without_gpu():
     assert lib.spmm_b200_destroy(h) == 0
 
 
+def test_argument_errors_are_status_codes_without_gpu():
+    """Entry points added in round 2 keep the ABI's contract — a status code and a message, never a crash or an exit —
+    also on a machine without a device."""
+    from hpc_b200._lib import lib
+    out = ctypes.c_void_p()
+    assert lib.spmm_b200_create_column_sorted(None, 32, None, ctypes.byref(out)) == -1
+    assert b"create_column_sorted" in lib.spmm_b200_last_error()
+    assert lib.spmm_b200_create_transposed(None, 32, None, ctypes.byref(out)) == -1
+    h = ctypes.c_void_p()
+    dummy = (ctypes.c_int * 6)()
+    assert lib.spmm_b200_create(dummy, None, None, 5, 0, 32, ctypes.byref(h)) == 0
+    assert lib.spmm_b200_create_column_sorted(h, -1, None, ctypes.byref(out)) == -1
+    assert lib.spmm_b200_destroy(h) == 0
+    rc = lib.spmm_b200_trim_memory()             # 0 with a device; the CUDA error code (and its text) without one
+    assert rc == 0 or lib.spmm_b200_last_error()
+
+
 def test_mg_create_rejects_bad_csr_without_gpu():
     """spmm_b200_mg_create validates the host CSR before it slices it (status code, no crash, no GPU needed for that)."""
     from hpc_b200._lib import lib
